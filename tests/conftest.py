@@ -1,0 +1,34 @@
+"""pytest configuration: registers the `gpu` marker and puts the repo root on sys.path."""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def rel_fro(a, b):
+    """relative Frobenius error ||a-b|| / ||b|| in float64"""
+    import torch
+
+    a64, b64 = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a64 - b64).norm() / b64.norm().clamp_min(1e-30))
