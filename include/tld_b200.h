@@ -1,0 +1,101 @@
+/* tld_b200.h — C ABI of libtld_b200.so, the B200-native (sm_100a) hot path of
+ * apapiu/transformer_latent_diffusion.
+ *
+ * The reference is pure Python and has NO FFI boundary of its own; its boundary is the
+ * Python class API.  Each entry point below therefore names the reference method whose body it replaces
+ * (paths relative to /root/reference).  The Python mirror of that API lives in
+ * transformer_latent_diffusion_b200/{denoiser,diffusion}.py and binds these symbols with ctypes
+ * (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer unless stated otherwise
+ *   - all tensors are contiguous, row-major, fp32 at the boundary (the reference's default dtype);
+ *     bf16 exists only inside the library as the tensor-core operand format (fp32 accumulate)
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); calls on one handle are not re-entrant
+ *   - return 0 on success; non-zero on error, message via tld_last_error() (thread-local)
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns an error
+ */
+#ifndef TLD_B200_H
+#define TLD_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define TLD_API __attribute__((visibility("default")))
+#else
+#define TLD_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tld_denoiser tld_denoiser; /* opaque */
+
+/* Constructor arguments of tld.denoiser.Denoiser (tld/denoiser.py:86-97).  dropout is accepted for
+ * signature parity and must be 0 for the inference path (the reference evaluates with model.eval()). */
+typedef struct tld_config {
+  int32_t image_size;       /* latent H = W                         */
+  int32_t noise_embed_dims; /* sinusoidal embedding width E         */
+  int32_t patch_size;
+  int32_t embed_dim;        /* D, multiple of 128, heads = D/64     */
+  int32_t n_layers;
+  int32_t text_emb_size;
+  int32_t mlp_multiplier;
+  int32_t n_channels;
+  float dropout;
+} tld_config;
+
+TLD_API const char* tld_last_error(void);
+TLD_API int tld_version(void);
+
+/* ---- lifetime --------------------------------------------------------------------------------
+ * Replaces Denoiser.__init__ + .to(device) (tld/denoiser.py:86-114, tld/diffusion.py:145-155). */
+TLD_API int tld_denoiser_create(const tld_config* cfg, int device, tld_denoiser** out);
+TLD_API void tld_denoiser_destroy(tld_denoiser* h);
+
+/* Replaces load_state_dict for ONE entry (tld/diffusion.py:152-153).  `key` is the reference state_dict key
+ * (e.g. "denoiser_trans_block.decoder_blocks.0.mlp.mlp.1.weight"); `data` is fp32 (host or device pointer,
+ * `numel` elements).  The library copies/packs into its own arena (bf16 for GEMM operands, fp32 otherwise). */
+TLD_API int tld_denoiser_set_param(tld_denoiser* h, const char* key, const float* data, int64_t numel);
+/* Number of parameters still missing after the set_param calls (0 = ready). */
+TLD_API int tld_denoiser_missing_params(tld_denoiser* h);
+
+/* ---- Denoiser.forward (tld/denoiser.py:116-126) ---------------------------------------------
+ * x[B,C,H,W], noise_level[B,1], label[B,text_emb] -> out[B,C,H,W]; all fp32 device pointers. */
+TLD_API int tld_denoiser_forward(tld_denoiser* h, const float* x, const float* noise_level, const float* label,
+                         float* out, int batch, void* stream);
+
+/* ---- DiffusionGenerator.generate minus the VAE decode (tld/diffusion.py:29-89) --------------
+ * labels[num_imgs,text_emb] (the cond half; the zero uncond half is implicit, diffusion.py:61),
+ * seeds[num_imgs,C,H,W] initial noise (diffusion.py:105-120), latent_out[num_imgs,C,H,W] = final x0_pred.
+ * noise_levels: HOST pointer to n_levels floats or NULL for the default schedule
+ * 1 - linspace(0,1,n_iter)^exponent (diffusion.py:50-52; [0] is forced to 0.99 either way).
+ * One diffusion step (2B-sample CFG forward + guidance + multistep update) is one CUDA-graph launch. */
+TLD_API int tld_sampler_generate(tld_denoiser* h, const float* labels, const float* seeds, float* latent_out,
+                         int num_imgs, int n_iter, float class_guidance, float exponent, float sharp_f,
+                         float bright_f, int use_ddpm_plus, const float* noise_levels, int n_levels,
+                         void* stream);
+/* Device time of the sampling loop of the last tld_sampler_generate call (ms, CUDA events) and number of
+ * kernel launches (graph nodes x replays + prologue) it issued. */
+TLD_API int tld_sampler_last_stats(tld_denoiser* h, float* loop_ms, int64_t* kernel_launches);
+
+/* ---- single ops, exported for the parity tests (tests/test_ops_gpu.py) -----------------------
+ * Same kernels the forward uses, one at a time.  bf16 tensors are passed as raw uint16 device pointers. */
+/* out = A[M,K] * W[N,K]^T with epilogue `epi`: 0 bf16 | 1 +bias bf16 | 2 x_f32 += acc+bias | 4 f32 */
+TLD_API int tld_op_gemm(int epi, const uint16_t* A, const uint16_t* W, int M, int N, int K, void* out,
+                const float* bias, void* stream);
+/* q-projection GEMM fused with the 2-key cross-attention and residual add (transformer_blocks.py:70-72,137):
+ * x[M,D] += softmax2(q k0, q k1)(v0,v1) with q = A Wq^T; kv0/kv1 [rows, 2D] fp32 (K | V). */
+TLD_API int tld_op_gemm_xattn(const uint16_t* A, const uint16_t* Wq, int M, int D, float* x, const float* kv0,
+                      const float* kv1, int n_tok, void* stream);
+TLD_API int tld_op_layernorm(const float* x, const float* gamma, const float* beta, uint16_t* y, int rows, int D,
+                     void* stream);
+TLD_API int tld_op_self_attention(const uint16_t* qkv, float* x, int batch, int n_tok, int D, void* stream);
+TLD_API int tld_op_dwconv_gelu(const uint16_t* h, const float* w9, const float* bias, uint16_t* g, int batch, int grid,
+                       int channels, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TLD_B200_H */

@@ -33,10 +33,10 @@ FWD_CASES = {
 
 SAMPLER_CASES = {
     # name: (cfg, num_imgs, wseed, kwargs)
-    "gen_dpmpp": (O.OracleCfg(image_size=16, embed_dim=64, n_layers=2), 2, 11,
+    "gen_dpmpp": (O.OracleCfg(image_size=16, embed_dim=128, n_layers=2), 2, 11,
                   dict(n_iter=6, class_guidance=3.0, exponent=1, sharp_f=0.1, bright_f=0.1,
                        use_ddpm_plus=True)),
-    "gen_ddim_exp2": (O.OracleCfg(image_size=16, embed_dim=64, n_layers=2), 3, 12,
+    "gen_ddim_exp2": (O.OracleCfg(image_size=16, embed_dim=128, n_layers=2), 3, 12,
                       dict(n_iter=5, class_guidance=6.0, exponent=2, sharp_f=0.0, bright_f=0.0,
                            use_ddpm_plus=False)),
     "gen_custom_levels": (O.OracleCfg(image_size=16, embed_dim=128, n_layers=1), 1, 13,

@@ -1,0 +1,154 @@
+"""Single-kernel parity: every CUDA kernel of libtld_b200 (through its C-ABI `tld_op_*` entry point) against a
+plain PyTorch fp32 statement of the same op on the same inputs.
+
+Tolerances: operands are bf16-rounded BEFORE the reference is computed, accumulation is fp32 on both sides, so
+fp32-output ops must agree to ~1e-5 relative; bf16-output ops to one bf16 ulp (2^-8 relative).
+"""
+import math
+
+import pytest
+import torch
+
+from conftest import rel_fro
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from transformer_latent_diffusion_b200 import _lib
+
+    return _lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _bf16_bits(t):
+    return t.view(torch.int16)
+
+
+def _err_map(got, ref, bm=32, bn=32):
+    """coarse map of where the error lives (helps diagnosing tile/descriptor bugs)"""
+    d = (got.double() - ref.double()).abs()
+    M, N = d.shape
+    rows = []
+    for i in range(0, min(M, 256), bm):
+        rows.append(" ".join(f"{d[i:i + bm, j:j + bn].max().item():8.2e}" for j in range(0, min(N, 256), bn)))
+    return "\n".join(rows)
+
+
+GEMM_SHAPES = [
+    # (M, N, K)
+    (128, 64, 64), (128, 128, 64), (128, 256, 128), (256, 192, 256), (128, 768, 768),
+    (384, 2304, 768), (512, 3072, 768), (256, 768, 3072), (200, 256, 256), (64, 384, 128),
+    (4096, 768, 768),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("epi", [0, 4])
+def test_gemm_plain(lib, M, N, K, epi):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    ref = A.float() @ W.float().t()
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16 if epi == 0 else torch.float32)
+    lib.check(lib.load().tld_op_gemm(epi, lib.ptr(A), lib.ptr(W), M, N, K, lib.ptr(out), None, _stream()), "gemm")
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all(), "non-finite / unwritten outputs\n" + _err_map(out.float().nan_to_num(1e9), ref)
+    err = rel_fro(out.float(), ref)
+    tol = 4e-3 if epi == 0 else 2e-5
+    assert err < tol, f"rel_fro={err:.3e}\n" + _err_map(out.float(), ref)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 1024, 256), (384, 3072, 768)])
+def test_gemm_bias_bf16(lib, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = A.float() @ W.float().t() + bias
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    lib.check(lib.load().tld_op_gemm(1, lib.ptr(A), lib.ptr(W), M, N, K, lib.ptr(out), lib.ptr(bias), _stream()), "gemm")
+    assert rel_fro(out.float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 1024), (384, 768, 3072), (130, 128, 512)])
+def test_gemm_bias_residual(lib, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(2)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    x = torch.randn(M, N, device="cuda", generator=g)
+    ref = x + A.float() @ W.float().t() + bias
+    lib.check(lib.load().tld_op_gemm(2, lib.ptr(A), lib.ptr(W), M, N, K, lib.ptr(x), lib.ptr(bias), _stream()), "gemm")
+    assert rel_fro(x, ref) < 2e-5, _err_map(x, ref)
+
+
+@pytest.mark.parametrize("B,n_tok,D", [(2, 64, 128), (3, 64, 128), (2, 256, 256), (3, 256, 768), (1, 1024, 128)])
+def test_gemm_cross_attention_epilogue(lib, B, n_tok, D):
+    """q_linear + 2-key SDPA + residual (transformer_blocks.py:70-72,137) fused in the GEMM epilogue."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    M = B * n_tok
+    A = torch.randn(M, D, device="cuda", generator=g).bfloat16()
+    Wq = (torch.randn(D, D, device="cuda", generator=g) / math.sqrt(D)).bfloat16()
+    kv0 = torch.randn(B, 2 * D, device="cuda", generator=g)
+    kv1 = torch.randn(B, 2 * D, device="cuda", generator=g)
+    x = torch.randn(M, D, device="cuda", generator=g)
+    H = D // 64
+    q = (A.float() @ Wq.float().t()).view(B, n_tok, H, 64)
+    k = torch.stack([kv0[:, :D], kv1[:, :D]], 1).view(B, 2, H, 64)
+    v = torch.stack([kv0[:, D:], kv1[:, D:]], 1).view(B, 2, H, 64)
+    s = torch.einsum("bnhd,bshd->bhns", q, k) / 8.0
+    o = torch.einsum("bhns,bshd->bnhd", torch.softmax(s, -1), v).reshape(M, D)
+    ref = x + o
+    lib.check(lib.load().tld_op_gemm_xattn(lib.ptr(A), lib.ptr(Wq), M, D, lib.ptr(x), lib.ptr(kv0), lib.ptr(kv1), n_tok,
+                                           _stream()), "gemm_xattn")
+    assert rel_fro(x, ref) < 1e-4, _err_map(x, ref)
+
+
+@pytest.mark.parametrize("rows,D", [(8, 128), (13, 256), (1000, 768), (5, 1024)])
+def test_layernorm(lib, rows, D):
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn(rows, D, device="cuda", generator=g) * 3 + 1.5
+    w = torch.randn(D, device="cuda", generator=g)
+    b = torch.randn(D, device="cuda", generator=g)
+    ref = torch.nn.functional.layer_norm(x, (D,), w, b, 1e-5)
+    y = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
+    lib.check(lib.load().tld_op_layernorm(lib.ptr(x), lib.ptr(w), lib.ptr(b), lib.ptr(y), rows, D, _stream()), "ln")
+    assert (y.float() - ref).abs().max() <= 2 ** -8 * ref.abs().max() + 1e-6
+    assert rel_fro(y.float(), ref) < 3e-3
+
+
+@pytest.mark.parametrize("B,n_tok,D", [(1, 64, 128), (2, 256, 128), (3, 256, 768), (1, 1024, 256), (1, 4096, 128)])
+def test_self_attention(lib, B, n_tok, D):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    T = B * n_tok
+    qkv = torch.randn(T, 3 * D, device="cuda", generator=g).bfloat16()
+    x = torch.randn(T, D, device="cuda", generator=g)
+    H = D // 64
+    q, k, v = (t.float().view(B, n_tok, H, 64).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=1))
+    s = (q @ k.transpose(-1, -2)) / 8.0
+    o = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(T, D)
+    ref = x + o
+    lib.check(lib.load().tld_op_self_attention(lib.ptr(qkv), lib.ptr(x), B, n_tok, D, _stream()), "attn")
+    # P is rounded to bf16 before the PV product (as in every flash kernel): error ~2^-9 relative on o
+    assert rel_fro(x - (ref - o), o) < 6e-3, _err_map(x, ref)
+
+
+@pytest.mark.parametrize("B,grid,C", [(1, 8, 512), (2, 16, 1024), (2, 16, 3072), (1, 32, 512)])
+def test_dwconv_gelu(lib, B, grid, C):
+    g = torch.Generator(device="cuda").manual_seed(6)
+    h = torch.randn(B, grid, grid, C, device="cuda", generator=g).bfloat16()
+    w = torch.randn(C, 1, 3, 3, device="cuda", generator=g) / 3
+    bias = torch.randn(C, device="cuda", generator=g) * 0.1
+    ref = torch.nn.functional.conv2d(h.float().permute(0, 3, 1, 2), w, bias, padding=1, groups=C)
+    ref = torch.nn.functional.gelu(ref).permute(0, 2, 3, 1).contiguous()
+    w9 = w.view(C, 9).t().contiguous()
+    out = torch.empty_like(h)
+    lib.check(lib.load().tld_op_dwconv_gelu(lib.ptr(h), lib.ptr(w9), lib.ptr(bias), lib.ptr(out), B, grid, C, _stream()),
+              "dwconv")
+    assert rel_fro(out.float(), ref) < 3e-3
+    assert (out.float() - ref).abs().max() <= 2 ** -8 * ref.abs().max() + 1e-5

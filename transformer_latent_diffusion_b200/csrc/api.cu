@@ -1,0 +1,571 @@
+// C ABI of libtld_b200.so (include/tld_b200.h): handle, weight packing, Denoiser.forward, CFG sampler.
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/tld_b200.h"
+#include "common.h"
+#include "gemm_tcgen05.cuh"  // EpiMode
+
+namespace tld {
+
+static thread_local std::string g_err;
+int fail(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+const char* last_error() { return g_err.c_str(); }
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------ packing
+__global__ void f32_to_bf16_kernel(const float* __restrict__ s, bf16* __restrict__ d, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = __float2bfloat16(s[i]);
+}
+__global__ void transpose_f32_kernel(const float* __restrict__ s, float* __restrict__ d, int rows, int cols) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // d[c][r] = s[r][c]
+  if (i < (long long)rows * cols) {
+    const int r = int(i / cols), c = int(i % cols);
+    d[(size_t)c * rows + r] = s[i];
+  }
+}
+
+enum PackKind { P_F32, P_BF16, P_TRANSPOSE_F32 };
+struct Slot {
+  PackKind kind;
+  void* dst;
+  long long numel;
+  int rows, cols;  // for P_TRANSPOSE_F32: source is [rows, cols]
+  bool filled;
+};
+
+}  // namespace tld
+
+using namespace tld;
+
+struct tld_denoiser {
+  tld_config cfg;
+  int device;
+  int D, L, N, G, pd, H4, E, Te, C, img, patch;
+  std::map<std::string, Slot> slots;
+  std::vector<void*> allocs;
+  float* staging = nullptr;
+  long long staging_elems = 0;
+
+  // parameters (device)
+  CondW cond;
+  EmbedW emb;
+  float *out_w, *out_b;
+  struct Layer {
+    bf16 *wqkv, *wq, *wup, *wdown;
+    float *ln1w, *ln1b, *ln2w, *ln2b, *ln3w, *ln3b, *bup, *dww9, *dwb, *bdown;
+  };
+  std::vector<Layer> layers;
+  bf16* wkv_all = nullptr;  // [L*2D, D]
+
+  // activation workspace, sized for ws_batch samples
+  int ws_batch = 0;
+  float* x_res = nullptr;   // [T, D] fp32 residual stream
+  bf16* xn = nullptr;       // [T, D]
+  bf16* qkv = nullptr;      // [T, 3D]
+  bf16* hid = nullptr;      // [T, 4D]
+  bf16* hid2 = nullptr;     // [T, 4D]
+  float* model_out = nullptr;  // [B, C, H, W]
+  // conditioning workspace
+  int ws_cond_rows = 0;
+  bf16* ycond = nullptr;    // [rows, D]
+  float* kv = nullptr;      // [rows, L*2D]
+  float* tlevels = nullptr; // [max steps]
+
+  // sampler state
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  float *x_t = nullptr, *x0_prev = nullptr, *x0_out = nullptr;
+  int sampler_batch = 0;
+  StepCoef* step_table = nullptr;
+  int step_table_cap = 0;
+  int* step_ptr = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_batch = -1;
+  float last_loop_ms = 0.f;
+  long long last_launches = 0;
+};
+
+namespace tld {
+
+template <typename T>
+static int dev_alloc(tld_denoiser* h, T** p, long long n, bool track = true) {
+  void* q = nullptr;
+  TLD_CUDA_OK(cudaMalloc(&q, (size_t)(n > 0 ? n : 1) * sizeof(T)));
+  *p = reinterpret_cast<T*>(q);
+  if (track) h->allocs.push_back(q);
+  return 0;
+}
+
+static int add_slot(tld_denoiser* h, const std::string& key, PackKind kind, void* dst, long long numel, int rows = 0,
+                    int cols = 0) {
+  h->slots[key] = Slot{kind, dst, numel, rows, cols, false};
+  return 0;
+}
+
+template <typename T>
+static int alloc_slot(tld_denoiser* h, const std::string& key, PackKind kind, T** dst, long long numel, int rows = 0,
+                      int cols = 0) {
+  if (dev_alloc(h, dst, numel)) return 1;
+  return add_slot(h, key, kind, *dst, numel, rows, cols);
+}
+
+static int build_params(tld_denoiser* h) {
+  const int D = h->D, L = h->L, N = h->N, pd = h->pd, H4 = h->H4, E = h->E, Te = h->Te;
+  const std::string tb = "denoiser_trans_block.";
+  float* f = nullptr;
+#define F32(key, field, n)                                   \
+  if (alloc_slot(h, key, P_F32, &f, (n))) return 1;          \
+  field = f;
+  F32("fourier_feats.0.angular_speeds", h->cond.speeds, E / 2)
+  F32("fourier_feats.1.weight", h->cond.w1, (long long)D * E)
+  F32("fourier_feats.1.bias", h->cond.b1, D)
+  F32("fourier_feats.3.weight", h->cond.w2, (long long)D * D)
+  F32("fourier_feats.3.bias", h->cond.b2, D)
+  F32("label_proj.weight", h->cond.wl, (long long)D * Te)
+  F32("label_proj.bias", h->cond.bl, D)
+  F32("norm.weight", h->cond.ln_w, D)
+  F32("norm.bias", h->cond.ln_b, D)
+  F32(tb + "patchify_and_embed.0.weight", h->emb.conv_w, (long long)pd * pd)
+  F32(tb + "patchify_and_embed.0.bias", h->emb.conv_b, pd)
+  F32(tb + "patchify_and_embed.2.weight", h->emb.ln1_w, pd)
+  F32(tb + "patchify_and_embed.2.bias", h->emb.ln1_b, pd)
+  F32(tb + "patchify_and_embed.3.bias", h->emb.lin_b, D)
+  F32(tb + "patchify_and_embed.4.weight", h->emb.ln2_w, D)
+  F32(tb + "patchify_and_embed.4.bias", h->emb.ln2_b, D)
+  F32(tb + "pos_embed.weight", h->emb.pos, (long long)N * D)
+  F32(tb + "out_proj.0.weight", h->out_w, (long long)pd * D)
+  F32(tb + "out_proj.0.bias", h->out_b, pd)
+  {
+    float* t = nullptr;
+    if (alloc_slot(h, tb + "patchify_and_embed.3.weight", P_TRANSPOSE_F32, &t, (long long)D * pd, D, pd)) return 1;
+    h->emb.lin_wT = t;
+  }
+  if (dev_alloc(h, &h->wkv_all, (long long)L * 2 * D * D)) return 1;
+  h->layers.resize(L);
+  for (int l = 0; l < L; ++l) {
+    auto& ly = h->layers[l];
+    const std::string b = tb + "decoder_blocks." + std::to_string(l) + ".";
+    if (alloc_slot(h, b + "self_attention.qkv_linear.weight", P_BF16, &ly.wqkv, 3LL * D * D)) return 1;
+    if (alloc_slot(h, b + "cross_attention.q_linear.weight", P_BF16, &ly.wq, (long long)D * D)) return 1;
+    add_slot(h, b + "cross_attention.kv_linear.weight", P_BF16, h->wkv_all + (size_t)l * 2 * D * D, 2LL * D * D);
+    if (alloc_slot(h, b + "mlp.mlp.0.weight", P_BF16, &ly.wup, (long long)H4 * D)) return 1;
+    if (alloc_slot(h, b + "mlp.mlp.3.weight", P_BF16, &ly.wdown, (long long)D * H4)) return 1;
+    F32(b + "mlp.mlp.0.bias", ly.bup, H4)
+    F32(b + "mlp.mlp.1.bias", ly.dwb, H4)
+    F32(b + "mlp.mlp.3.bias", ly.bdown, D)
+    F32(b + "norm1.weight", ly.ln1w, D)
+    F32(b + "norm1.bias", ly.ln1b, D)
+    F32(b + "norm2.weight", ly.ln2w, D)
+    F32(b + "norm2.bias", ly.ln2b, D)
+    F32(b + "norm3.weight", ly.ln3w, D)
+    F32(b + "norm3.bias", ly.ln3b, D)
+    float* t = nullptr;  // depthwise weight [4D,1,3,3] -> tap-major [9, 4D]
+    if (alloc_slot(h, b + "mlp.mlp.1.weight", P_TRANSPOSE_F32, &t, 9LL * H4, H4, 9)) return 1;
+    ly.dww9 = t;
+  }
+#undef F32
+  h->staging_elems = 0;
+  for (auto& kv : h->slots) h->staging_elems = kv.second.numel > h->staging_elems ? kv.second.numel : h->staging_elems;
+  return dev_alloc(h, &h->staging, h->staging_elems);
+}
+
+static void free_workspace(tld_denoiser* h) {
+  void* ptrs[] = {h->x_res, h->xn, h->qkv, h->hid, h->hid2, h->model_out};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  h->x_res = nullptr; h->xn = nullptr; h->qkv = nullptr; h->hid = nullptr; h->hid2 = nullptr; h->model_out = nullptr;
+  h->ws_batch = 0;
+  if (h->graph_exec) {
+    cudaGraphExecDestroy(h->graph_exec);
+    h->graph_exec = nullptr;
+    h->graph_batch = -1;
+  }
+}
+
+static int ensure_workspace(tld_denoiser* h, int batch) {
+  if (batch <= h->ws_batch) return 0;
+  TLD_CUDA_OK(cudaDeviceSynchronize());
+  free_workspace(h);
+  const long long T = (long long)batch * h->N;
+  if (dev_alloc(h, &h->x_res, T * h->D, false)) return 1;
+  if (dev_alloc(h, &h->xn, T * h->D, false)) return 1;
+  if (dev_alloc(h, &h->qkv, T * 3 * h->D, false)) return 1;
+  if (dev_alloc(h, &h->hid, T * h->H4, false)) return 1;
+  if (dev_alloc(h, &h->hid2, T * h->H4, false)) return 1;
+  if (dev_alloc(h, &h->model_out, (long long)batch * h->C * h->img * h->img, false)) return 1;
+  h->ws_batch = batch;
+  return 0;
+}
+
+static int ensure_cond(tld_denoiser* h, int rows) {
+  if (rows <= h->ws_cond_rows) return 0;
+  TLD_CUDA_OK(cudaDeviceSynchronize());
+  if (h->ycond) cudaFree(h->ycond);
+  if (h->kv) cudaFree(h->kv);
+  if (h->tlevels) cudaFree(h->tlevels);
+  h->ycond = nullptr; h->kv = nullptr; h->tlevels = nullptr;
+  if (h->graph_exec) {
+    cudaGraphExecDestroy(h->graph_exec);
+    h->graph_exec = nullptr;
+    h->graph_batch = -1;
+  }
+  const int r = ((rows + 127) / 128) * 128;
+  if (dev_alloc(h, &h->ycond, (long long)r * h->D, false)) return 1;
+  if (dev_alloc(h, &h->kv, (long long)r * h->L * 2 * h->D, false)) return 1;
+  if (dev_alloc(h, &h->tlevels, r, false)) return 1;
+  h->ws_cond_rows = r;
+  return 0;
+}
+
+// The L decoder blocks + output projection on the tokens already in h->x_res (transformer_blocks.py:135-139).
+static int run_blocks(tld_denoiser* h, int batch, const float* kv0, long long kv0_stride, const float* kv1,
+                      long long kv1_stride, const int* step_ptr, float* out, cudaStream_t st) {
+  const int D = h->D, H4 = h->H4, N = h->N;
+  const int T = batch * N;
+  for (int l = 0; l < h->L; ++l) {
+    const auto& ly = h->layers[l];
+    // x = SelfAttention(LN1(x)) + x
+    if (launch_layernorm_bf16(h->x_res, ly.ln1w, ly.ln1b, h->xn, T, D, st)) return 1;
+    if (launch_gemm(EPI_BF16, h->xn, D, ly.wqkv, D, T, 3 * D, D, h->qkv, 3 * D, nullptr, nullptr, st)) return 1;
+    if (launch_self_attention(h->qkv, h->x_res, batch, N, D, st)) return 1;
+    // x = CrossAttention(LN2(x), y) + x
+    if (launch_layernorm_bf16(h->x_res, ly.ln2w, ly.ln2b, h->xn, T, D, st)) return 1;
+    XattnArgs xa;
+    xa.kv0 = kv0 + (size_t)l * 2 * D;
+    xa.kv1 = kv1 + (size_t)l * 2 * D;
+    xa.kv0_stride = kv0_stride;
+    xa.kv1_stride = kv1_stride;
+    xa.step_ptr = step_ptr;
+    xa.n_tok = N;
+    xa.embed_dim = D;
+    if (launch_gemm(EPI_XATTN_RESID_F32, h->xn, D, ly.wq, D, T, D, D, h->x_res, D, nullptr, &xa, st)) return 1;
+    // x = MLPSepConv(LN3(x)) + x
+    if (launch_layernorm_bf16(h->x_res, ly.ln3w, ly.ln3b, h->xn, T, D, st)) return 1;
+    if (launch_gemm(EPI_BIAS_BF16, h->xn, D, ly.wup, D, T, H4, D, h->hid, H4, ly.bup, nullptr, st)) return 1;
+    if (launch_dwconv_gelu(h->hid, ly.dww9, ly.dwb, h->hid2, batch, h->G, H4, st)) return 1;
+    if (launch_gemm(EPI_BIAS_RESID_F32, h->hid2, H4, ly.wdown, H4, T, D, H4, h->x_res, D, ly.bdown, nullptr, st))
+      return 1;
+  }
+  return launch_outproj(h->x_res, h->out_w, h->out_b, out, batch, h->C, h->img, h->patch, D, st);
+}
+
+static int kernels_per_forward(const tld_denoiser* h) { return 1 + 9 * h->L + 1; }
+
+}  // namespace tld
+
+// =========================================================================================== C ABI
+extern "C" {
+
+const char* tld_last_error(void) { return tld::last_error(); }
+int tld_version(void) { return 1; }
+
+int tld_denoiser_create(const tld_config* cfg, int device, tld_denoiser** out) {
+  TLD_CHECK(cfg && out, "tld_denoiser_create: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail("tld_denoiser_create: no CUDA device (this library has no CPU fallback)");
+  TLD_CHECK(device >= 0 && device < ndev, "tld_denoiser_create: bad device index");
+  TLD_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  TLD_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  TLD_CHECK(prop.major == 10, "tld_denoiser_create: kernels are built for sm_100a (B200) only, found sm_" +
+                                  std::to_string(prop.major) + std::to_string(prop.minor));
+  TLD_CHECK(cfg->embed_dim % 128 == 0 && cfg->embed_dim >= 128 && cfg->embed_dim <= 1024,
+            "embed_dim must be a multiple of 128 in [128,1024]");
+  TLD_CHECK(cfg->patch_size > 0 && cfg->image_size % cfg->patch_size == 0, "image_size must be divisible by patch_size");
+  const int G = cfg->image_size / cfg->patch_size;
+  TLD_CHECK((G * G) % 64 == 0, "tokens per sample ((image_size/patch_size)^2) must be a multiple of 64");
+  TLD_CHECK(cfg->n_channels * cfg->patch_size * cfg->patch_size <= 64, "n_channels*patch_size^2 must be <= 64");
+  TLD_CHECK(cfg->noise_embed_dims % 2 == 0 && cfg->noise_embed_dims > 0, "noise_embed_dims must be even");
+  TLD_CHECK(cfg->n_layers > 0 && cfg->mlp_multiplier > 0 && cfg->text_emb_size > 0, "bad layer configuration");
+  TLD_CHECK((cfg->mlp_multiplier * cfg->embed_dim) % 64 == 0, "mlp width must be a multiple of 64");
+  TLD_CHECK(cfg->dropout == 0.f, "dropout must be 0 on the inference path");
+  tld_denoiser* h = new tld_denoiser();
+  h->cfg = *cfg;
+  h->device = device;
+  h->D = cfg->embed_dim; h->L = cfg->n_layers; h->G = G; h->N = G * G;
+  h->C = cfg->n_channels; h->patch = cfg->patch_size; h->img = cfg->image_size;
+  h->pd = h->C * h->patch * h->patch; h->H4 = cfg->mlp_multiplier * h->D;
+  h->E = cfg->noise_embed_dims; h->Te = cfg->text_emb_size;
+  if (build_params(h)) { tld_denoiser_destroy(h); return 1; }
+  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreate(&h->ev_t0) != cudaSuccess || cudaEventCreate(&h->ev_t1) != cudaSuccess) {
+    tld_denoiser_destroy(h);
+    return fail("tld_denoiser_create: stream/event creation failed");
+  }
+  if (dev_alloc(h, &h->step_ptr, 1)) { tld_denoiser_destroy(h); return 1; }
+  *out = h;
+  return 0;
+}
+
+void tld_denoiser_destroy(tld_denoiser* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  free_workspace(h);
+  for (void* p : h->allocs) cudaFree(p);
+  void* extra[] = {h->ycond, h->kv, h->tlevels, h->x_t, h->x0_prev, h->x0_out, h->step_table};
+  for (void* p : extra)
+    if (p) cudaFree(p);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  cudaEvent_t evs[] = {h->ev_in, h->ev_out, h->ev_t0, h->ev_t1};
+  for (cudaEvent_t e : evs)
+    if (e) cudaEventDestroy(e);
+  delete h;
+}
+
+int tld_denoiser_set_param(tld_denoiser* h, const char* key, const float* data, int64_t numel) {
+  TLD_CHECK(h && key && data, "tld_denoiser_set_param: null argument");
+  TLD_CUDA_OK(cudaSetDevice(h->device));
+  auto it = h->slots.find(key);
+  if (it == h->slots.end()) return fail(std::string("unexpected state_dict key: ") + key);
+  Slot& s = it->second;
+  if (numel != s.numel)
+    return fail(std::string("size mismatch for ") + key + ": got " + std::to_string(numel) + ", expected " +
+                std::to_string(s.numel));
+  const int thr = 256;
+  const int blocks = int((s.numel + thr - 1) / thr);
+  if (s.kind == P_F32) {
+    TLD_CUDA_OK(cudaMemcpy(s.dst, data, (size_t)numel * sizeof(float), cudaMemcpyDefault));
+  } else {
+    TLD_CUDA_OK(cudaMemcpy(h->staging, data, (size_t)numel * sizeof(float), cudaMemcpyDefault));
+    if (s.kind == P_BF16)
+      f32_to_bf16_kernel<<<blocks, thr>>>(h->staging, reinterpret_cast<bf16*>(s.dst), s.numel);
+    else
+      transpose_f32_kernel<<<blocks, thr>>>(h->staging, reinterpret_cast<float*>(s.dst), s.rows, s.cols);
+    TLD_CUDA_OK(cudaGetLastError());
+    TLD_CUDA_OK(cudaDeviceSynchronize());
+  }
+  s.filled = true;
+  return 0;
+}
+
+int tld_denoiser_missing_params(tld_denoiser* h) {
+  if (!h) return -1;
+  int n = 0;
+  for (auto& kv : h->slots) n += kv.second.filled ? 0 : 1;
+  return n;
+}
+
+int tld_denoiser_forward(tld_denoiser* h, const float* x, const float* noise_level, const float* label, float* out,
+                         int batch, void* stream) {
+  TLD_CHECK(h && x && noise_level && label && out, "tld_denoiser_forward: null argument");
+  TLD_CHECK(batch > 0, "tld_denoiser_forward: batch must be positive");
+  TLD_CHECK(tld_denoiser_missing_params(h) == 0, "tld_denoiser_forward: parameters missing (call tld_denoiser_set_param for every state_dict key)");
+  TLD_CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (ensure_workspace(h, batch) || ensure_cond(h, 2 * batch)) return 1;
+  const long long kvs = (long long)h->L * 2 * h->D;
+  // conditioning tokens: rows [0,B) noise token, rows [B,2B) label token (denoiser.py:117-122)
+  if (launch_cond_noise(noise_level, batch, h->E, h->D, h->cond, h->ycond, st)) return 1;
+  if (launch_cond_label(label, batch, batch, h->Te, h->D, h->cond, h->ycond + (size_t)batch * h->D, st)) return 1;
+  // K|V of both cond tokens for every layer in one GEMM (transformer_blocks.py:71)
+  if (launch_gemm(EPI_F32, h->ycond, h->D, h->wkv_all, h->D, 2 * batch, int(kvs), h->D, h->kv, int(kvs), nullptr,
+                  nullptr, st))
+    return 1;
+  if (launch_embed(x, batch, batch, h->C, h->img, h->patch, h->D, h->emb, h->x_res, st)) return 1;
+  return run_blocks(h, batch, h->kv, kvs, h->kv + (size_t)batch * kvs, kvs, nullptr, out, st);
+}
+
+int tld_sampler_generate(tld_denoiser* h, const float* labels, const float* seeds, float* latent_out, int num_imgs,
+                         int n_iter, float class_guidance, float exponent, float sharp_f, float bright_f,
+                         int use_ddpm_plus, const float* noise_levels, int n_levels, void* stream) {
+  TLD_CHECK(h && labels && seeds && latent_out, "tld_sampler_generate: null argument");
+  TLD_CHECK(num_imgs > 0, "tld_sampler_generate: num_imgs must be positive");
+  TLD_CHECK(tld_denoiser_missing_params(h) == 0, "tld_sampler_generate: parameters missing");
+  TLD_CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t caller = reinterpret_cast<cudaStream_t>(stream);
+  cudaStream_t st = h->own_stream;
+
+  // ---- schedule on the host (diffusion.py:50-57), python-float (double) arithmetic
+  std::vector<double> sig;
+  if (noise_levels) {
+    TLD_CHECK(n_levels >= 2, "tld_sampler_generate: need at least 2 noise levels");
+    for (int i = 0; i < n_levels; ++i) sig.push_back((double)noise_levels[i]);
+  } else {
+    TLD_CHECK(n_iter >= 2, "tld_sampler_generate: n_iter must be >= 2");
+    const double step = 1.0 / n_iter;
+    const int n = (int)ceil((1.0 - 0.0) / step);  // torch.arange(0, 1, 1/n_iter) length
+    for (int i = 0; i < n; ++i) {
+      const float v = (float)(0.0 + i * step);     // fp32 arange value
+      sig.push_back((double)(1.0f - powf(v, exponent)));
+    }
+  }
+  sig[0] = 0.99;
+  const int calls = (int)sig.size();
+  std::vector<double> rs;
+  if (use_ddpm_plus) {
+    std::vector<double> lam(calls), hs;
+    for (int i = 0; i < calls; ++i) lam[i] = log((1.0 - sig[i]) / sig[i]);
+    for (int i = 1; i < calls; ++i) hs.push_back(lam[i] - lam[i - 1]);
+    for (size_t i = 1; i < hs.size(); ++i) rs.push_back(hs[i - 1] / hs[i]);
+  }
+  std::vector<StepCoef> table(calls);
+  std::vector<float> tl(calls);
+  for (int i = 0; i < calls; ++i) {
+    StepCoef sc{};
+    sc.guidance = class_guidance;
+    sc.one_minus_g = (float)(1.0 - (double)class_guidance);
+    sc.sharp = sharp_f;
+    sc.bright = bright_f;
+    if (i < calls - 1) {
+      const double cur = sig[i], next = sig[i + 1];
+      tl[i] = (float)cur;
+      sc.dsig = (float)(cur - next);
+      sc.next = (float)next;
+      sc.cur = (float)cur;
+      if (i > 0 && use_ddpm_plus) {
+        sc.c1 = (float)(1.0 + 1.0 / (2.0 * rs[i - 1]));
+        sc.c2 = (float)(1.0 / (2.0 * rs[i - 1]));
+      } else {
+        sc.c1 = 1.f;
+        sc.c2 = 0.f;
+      }
+    } else {
+      tl[i] = (float)sig[calls - 1];  // final prediction at next_noise (diffusion.py:85)
+      sc.is_final = 1;
+    }
+    table[i] = sc;
+  }
+
+  // ---- buffers
+  const int Beff = 2 * num_imgs;
+  const long long img_elems = (long long)num_imgs * h->C * h->img * h->img;
+  if (ensure_workspace(h, Beff) || ensure_cond(h, calls + Beff)) return 1;
+  if (num_imgs > h->sampler_batch) {
+    TLD_CUDA_OK(cudaDeviceSynchronize());
+    float** bufs[] = {&h->x_t, &h->x0_prev, &h->x0_out};
+    for (float** b : bufs) {
+      if (*b) cudaFree(*b);
+      if (dev_alloc(h, b, img_elems, false)) return 1;
+    }
+    h->sampler_batch = num_imgs;
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; h->graph_batch = -1; }
+  }
+  if (calls > h->step_table_cap) {
+    TLD_CUDA_OK(cudaDeviceSynchronize());
+    if (h->step_table) cudaFree(h->step_table);
+    if (dev_alloc(h, &h->step_table, calls, false)) return 1;
+    h->step_table_cap = calls;
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; h->graph_batch = -1; }
+  }
+
+  // order after the caller's stream
+  TLD_CUDA_OK(cudaEventRecord(h->ev_in, caller));
+  TLD_CUDA_OK(cudaStreamWaitEvent(st, h->ev_in, 0));
+  TLD_CUDA_OK(cudaMemcpyAsync(h->step_table, table.data(), sizeof(StepCoef) * calls, cudaMemcpyHostToDevice, st));
+  TLD_CUDA_OK(cudaMemcpyAsync(h->tlevels, tl.data(), sizeof(float) * calls, cudaMemcpyHostToDevice, st));
+  TLD_CUDA_OK(cudaMemsetAsync(h->step_ptr, 0, sizeof(int), st));
+  TLD_CUDA_OK(cudaMemcpyAsync(h->x_t, seeds, sizeof(float) * img_elems, cudaMemcpyDeviceToDevice, st));
+  TLD_CUDA_OK(cudaStreamSynchronize(st));  // host vectors go out of scope; the copies above are tiny
+
+  // ---- conditioning hoisted out of the loop: the noise token depends only on the step, the label token only
+  // on the sample.  rows [0,calls): noise tokens; rows [calls, calls+2B): label tokens.
+  const long long kvs = (long long)h->L * 2 * h->D;
+  if (launch_cond_noise(h->tlevels, calls, h->E, h->D, h->cond, h->ycond, st)) return 1;
+  if (launch_cond_label(labels, Beff, num_imgs, h->Te, h->D, h->cond, h->ycond + (size_t)calls * h->D, st)) return 1;
+  if (launch_gemm(EPI_F32, h->ycond, h->D, h->wkv_all, h->D, calls + Beff, int(kvs), h->D, h->kv, int(kvs), nullptr,
+                  nullptr, st))
+    return 1;
+  const float* kv0 = h->kv;
+  const float* kv1 = h->kv + (size_t)calls * kvs;
+
+  // ---- one diffusion step = one CUDA graph (embed of cat[x,x] -> L blocks -> out-proj -> CFG + update)
+  if (!h->graph_exec || h->graph_batch != num_imgs) {
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    TLD_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = launch_embed(h->x_t, num_imgs, Beff, h->C, h->img, h->patch, h->D, h->emb, h->x_res, st);
+    if (!rc) rc = run_blocks(h, Beff, kv0, kvs /*row = *step_ptr*/, kv1, kvs, h->step_ptr, h->model_out, st);
+    if (!rc)
+      rc = launch_cfg_update(h->model_out, h->x_t, h->x0_prev, h->x0_out, h->step_table, h->step_ptr, num_imgs, h->C,
+                             h->img * h->img, st);
+    if (!rc) rc = launch_advance_step(h->step_ptr, st);
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
+    TLD_CUDA_OK(ce);
+    ce = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    TLD_CUDA_OK(ce);
+    h->graph_batch = num_imgs;
+  }
+  TLD_CUDA_OK(cudaEventRecord(h->ev_t0, st));
+  for (int i = 0; i < calls; ++i) TLD_CUDA_OK(cudaGraphLaunch(h->graph_exec, st));
+  TLD_CUDA_OK(cudaEventRecord(h->ev_t1, st));
+  TLD_CUDA_OK(cudaMemcpyAsync(latent_out, h->x0_out, sizeof(float) * img_elems, cudaMemcpyDeviceToDevice, st));
+  TLD_CUDA_OK(cudaEventRecord(h->ev_out, st));
+  TLD_CUDA_OK(cudaStreamWaitEvent(caller, h->ev_out, 0));
+  h->last_launches = (long long)calls * (kernels_per_forward(h) + 2) + 3;
+  h->last_loop_ms = -1.f;
+  return 0;
+}
+
+int tld_sampler_last_stats(tld_denoiser* h, float* loop_ms, int64_t* kernel_launches) {
+  TLD_CHECK(h, "tld_sampler_last_stats: null handle");
+  TLD_CUDA_OK(cudaSetDevice(h->device));
+  if (h->last_loop_ms < 0.f) {
+    TLD_CUDA_OK(cudaEventSynchronize(h->ev_t1));
+    TLD_CUDA_OK(cudaEventElapsedTime(&h->last_loop_ms, h->ev_t0, h->ev_t1));
+  }
+  if (loop_ms) *loop_ms = h->last_loop_ms;
+  if (kernel_launches) *kernel_launches = h->last_launches;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ single ops
+int tld_op_gemm(int epi, const uint16_t* A, const uint16_t* W, int M, int N, int K, void* out, const float* bias,
+                void* stream) {
+  TLD_CHECK(epi == EPI_BF16 || epi == EPI_BIAS_BF16 || epi == EPI_BIAS_RESID_F32 || epi == EPI_F32,
+            "tld_op_gemm: epilogue must be 0, 1, 2 or 4");
+  return launch_gemm(epi, reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(W), K, M, N, K, out, N,
+                     bias, nullptr, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int tld_op_gemm_xattn(const uint16_t* A, const uint16_t* Wq, int M, int D, float* x, const float* kv0,
+                      const float* kv1, int n_tok, void* stream) {
+  XattnArgs xa;
+  xa.kv0 = kv0; xa.kv1 = kv1;
+  xa.kv0_stride = 2LL * D; xa.kv1_stride = 2LL * D;
+  xa.step_ptr = nullptr; xa.n_tok = n_tok; xa.embed_dim = D;
+  return launch_gemm(EPI_XATTN_RESID_F32, reinterpret_cast<const bf16*>(A), D, reinterpret_cast<const bf16*>(Wq), D, M,
+                     D, D, x, D, nullptr, &xa, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int tld_op_layernorm(const float* x, const float* gamma, const float* beta, uint16_t* y, int rows, int D,
+                     void* stream) {
+  return launch_layernorm_bf16(x, gamma, beta, reinterpret_cast<bf16*>(y), rows, D,
+                               reinterpret_cast<cudaStream_t>(stream));
+}
+
+int tld_op_self_attention(const uint16_t* qkv, float* x, int batch, int n_tok, int D, void* stream) {
+  return launch_self_attention(reinterpret_cast<const bf16*>(qkv), x, batch, n_tok, D,
+                               reinterpret_cast<cudaStream_t>(stream));
+}
+
+int tld_op_dwconv_gelu(const uint16_t* hsrc, const float* w9, const float* bias, uint16_t* g, int batch, int grid,
+                       int channels, void* stream) {
+  return launch_dwconv_gelu(reinterpret_cast<const bf16*>(hsrc), w9, bias, reinterpret_cast<bf16*>(g), batch, grid,
+                            channels, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

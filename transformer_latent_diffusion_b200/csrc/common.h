@@ -1,0 +1,99 @@
+// Internal launcher declarations shared by the translation units of libtld_b200.so.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace tld {
+
+typedef __nv_bfloat16 bf16;
+
+// error plumbing: every launcher returns 0 or sets the thread-local message and returns non-zero
+int fail(const std::string& msg);
+const char* last_error();
+#define TLD_CUDA_OK(expr)                                                                      \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return ::tld::fail(std::string(#expr) + " -> " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
+                         std::to_string(__LINE__));                                            \
+  } while (0)
+#define TLD_CHECK(cond, msg)                  \
+  do {                                        \
+    if (!(cond)) return ::tld::fail(msg);     \
+  } while (0)
+
+int sm_count();
+
+// ---------------------------------------------------------------- gemm.cu
+struct XattnArgs {
+  const float* kv0;
+  const float* kv1;
+  long long kv0_stride, kv1_stride;
+  const int* step_ptr;
+  int n_tok;
+  int embed_dim;
+};
+// C[M,N] = A[M,K] * W[N,K]^T with a fused epilogue (see gemm_tcgen05.cuh). lda/ldw in elements.
+int launch_gemm(int epi, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, void* out, int ldo,
+                const float* bias, const XattnArgs* xa, cudaStream_t st);
+
+// ---------------------------------------------------------------- rowwise.cu
+int launch_layernorm_bf16(const float* x, const float* gamma, const float* beta, bf16* y, int rows, int D,
+                          cudaStream_t st);
+struct EmbedW {
+  const float* conv_w;  // [pd, pd] (out, in) with in = (c, p1, p2)
+  const float* conv_b;  // [pd]
+  const float* ln1_w;   // [pd]
+  const float* ln1_b;
+  const float* lin_wT;  // [pd, D]  (transposed nn.Linear weight)
+  const float* lin_b;   // [D]
+  const float* ln2_w;   // [D]
+  const float* ln2_b;
+  const float* pos;     // [N, D]
+};
+// x[Bx,C,H,W] fp32 -> tokens[Bout,N,D] fp32; sample b reads image b % Bx (CFG duplication)
+int launch_embed(const float* x, int Bx, int Bout, int C, int img, int patch, int D, const EmbedW& w, float* out,
+                 cudaStream_t st);
+struct CondW {
+  const float* speeds;  // [E/2]
+  const float* w1;      // [D, E]
+  const float* b1;
+  const float* w2;      // [D, D]
+  const float* b2;
+  const float* wl;      // [D, Te]
+  const float* bl;
+  const float* ln_w;    // [D]
+  const float* ln_b;
+};
+// noise token: y[r] = LN(W2 gelu(W1 sincos(t[r]) + b1) + b2)  -> bf16 [R, D]
+int launch_cond_noise(const float* t, int R, int E, int D, const CondW& w, bf16* y, cudaStream_t st);
+// label token: y[r] = LN(Wl label[r] + bl); label == nullptr or r >= R_real -> zero label (uncond half)
+int launch_cond_label(const float* label, int R, int R_real, int Te, int D, const CondW& w, bf16* y,
+                      cudaStream_t st);
+// g = gelu(dwconv3x3(h) + b) over the token grid; h,g bf16 [B, grid, grid, C]; w tap-major [9, C]
+int launch_dwconv_gelu(const bf16* h, const float* w9, const float* bias, bf16* g, int B, int grid, int C,
+                       cudaStream_t st);
+// tokens[B,N,D] fp32 -> Linear(D->pd)+bias -> unpatchify -> out[B,C,H,W] fp32
+int launch_outproj(const float* x, const float* w, const float* b, float* out, int B, int C, int img, int patch,
+                   int D, cudaStream_t st);
+
+struct StepCoef {  // one entry per model call of the sampler (device table)
+  float guidance, one_minus_g;
+  float c1, c2;        // D = c1*x0 - c2*x0_prev   (c2 == 0: D = x0)
+  float dsig, next, cur;  // x_t = (dsig*D + next*x_t)/cur
+  int is_final;        // last model call: emit x0 (+ channel shifts), no x_t update
+  float sharp, bright;
+};
+// model_out[2B,...] (cond first, uncond second) -> CFG combine -> multistep update of x_t / x0_prev / x0_out
+int launch_cfg_update(const float* model_out, float* x_t, float* x0_prev, float* x0_out, const StepCoef* table,
+                      const int* step_ptr, int B, int C, int hw, cudaStream_t st);
+int launch_advance_step(int* step_ptr, cudaStream_t st);
+
+// ---------------------------------------------------------------- attention.cu
+// x[T,D] fp32 += softmax(q k^T / 8) v per (sample, head); qkv bf16 [T,3D] (q | k | v), head_dim 64
+int launch_self_attention(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st);
+
+}  // namespace tld

@@ -1,0 +1,137 @@
+// Host side of the tcgen05 GEMM: TMA descriptor encoding, tile-shape selection, launch.
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "common.h"
+#include "gemm_tcgen05.cuh"
+
+namespace tld {
+
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+static int resolve_encode() {
+  static std::once_flag once;
+  static int status = 0;
+  std::call_once(once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || fn == nullptr) {
+      status = 1;
+      return;
+    }
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  });
+  return status;
+}
+
+// 2-D bf16 row-major tensor [rows, cols] (cols contiguous, leading dimension ld elements),
+// box = [box_rows, 64 cols], 128-byte swizzle, OOB reads zero-filled.
+static int make_tmap_bf16(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld,
+                          int box_rows) {
+  if (resolve_encode()) return fail("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed, CUresult=" + std::to_string((int)r));
+  return 0;
+}
+
+template <int BN, int EPI>
+static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpi& ep,
+                    cudaStream_t st) {
+  auto kern = gemm_bf16_tn_kernel<BN, EPI>;
+  constexpr int smem = GemmSmem<BN>::TOTAL;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TLD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, GEMM_THREADS, smem, st>>>(ta, tb, M, N, K, ep);
+  TLD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <int BN>
+static int launch_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpi& ep,
+                     cudaStream_t st) {
+  switch (epi) {
+    case EPI_BF16: return launch_t<BN, EPI_BF16>(ta, tb, M, N, K, ep, st);
+    case EPI_BIAS_BF16: return launch_t<BN, EPI_BIAS_BF16>(ta, tb, M, N, K, ep, st);
+    case EPI_BIAS_RESID_F32: return launch_t<BN, EPI_BIAS_RESID_F32>(ta, tb, M, N, K, ep, st);
+    case EPI_XATTN_RESID_F32: return launch_t<BN, EPI_XATTN_RESID_F32>(ta, tb, M, N, K, ep, st);
+    case EPI_F32: return launch_t<BN, EPI_F32>(ta, tb, M, N, K, ep, st);
+  }
+  return fail("launch_gemm: unknown epilogue " + std::to_string(epi));
+}
+
+// Tile width: the widest BN in {256,192,128,64} that divides N, preferring the one with the least
+// wave-quantisation loss on the persistent grid (ties -> wider tile, fewer A re-reads).
+static int pick_bn(int M, int N) {
+  const int cands[4] = {256, 192, 128, 64};
+  const int sms = sm_count();
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  int best = 0;
+  double best_cost = 1e30;
+  for (int bn : cands) {
+    if (N % bn != 0 && !(bn == 64)) continue;
+    const int n_tiles = (N + bn - 1) / bn;
+    const long long tiles = (long long)m_tiles * n_tiles;
+    const long long waves = (tiles + sms - 1) / sms;
+    // time ~ waves * (tile work ~ bn) ; small penalty for narrow tiles (epilogue/A re-read overhead)
+    const double cost = double(waves) * bn * (1.0 + 8.0 / bn);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+int launch_gemm(int epi, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, void* out, int ldo,
+                const float* bias, const XattnArgs* xa, cudaStream_t st) {
+  TLD_CHECK(M > 0 && N > 0 && K > 0, "launch_gemm: empty problem");
+  TLD_CHECK(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "launch_gemm: K/lda/ldw must be multiples of 8 (16-byte TMA rows)");
+  TLD_CHECK(N % 32 == 0, "launch_gemm: N must be a multiple of 32");
+  TLD_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+            "launch_gemm: operands must be 16-byte aligned");
+  if (epi == EPI_XATTN_RESID_F32) {
+    TLD_CHECK(xa != nullptr, "launch_gemm: cross-attention epilogue needs XattnArgs");
+    TLD_CHECK(N % 64 == 0 && xa->n_tok % 64 == 0, "launch_gemm: cross-attention epilogue needs N and n_tok multiples of 64");
+  }
+  if (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_RESID_F32) TLD_CHECK(bias != nullptr, "launch_gemm: bias epilogue without bias");
+  const int bn = pick_bn(M, N);
+  CUtensorMap ta, tb;
+  if (make_tmap_bf16(&ta, A, M, K, lda, GEMM_BM)) return 1;
+  if (make_tmap_bf16(&tb, W, N, K, ldw, bn)) return 1;
+  GemmEpi ep{};
+  ep.out = out;
+  ep.ldo = ldo;
+  ep.bias = bias;
+  ep.scale = 0.125f;  // 1/sqrt(64)
+  if (xa) {
+    ep.kv0 = xa->kv0;
+    ep.kv1 = xa->kv1;
+    ep.kv0_stride = xa->kv0_stride;
+    ep.kv1_stride = xa->kv1_stride;
+    ep.step_ptr = xa->step_ptr;
+    ep.n_tok = xa->n_tok;
+    ep.embed_dim = xa->embed_dim;
+  }
+  switch (bn) {
+    case 256: return launch_bn<256>(epi, ta, tb, M, N, K, ep, st);
+    case 192: return launch_bn<192>(epi, ta, tb, M, N, K, ep, st);
+    case 128: return launch_bn<128>(epi, ta, tb, M, N, K, ep, st);
+    case 64: return launch_bn<64>(epi, ta, tb, M, N, K, ep, st);
+  }
+  return fail("launch_gemm: no tile width for N=" + std::to_string(N));
+}
+
+}  // namespace tld

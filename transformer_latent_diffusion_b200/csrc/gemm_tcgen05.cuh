@@ -1,0 +1,309 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
+//
+//   A : bf16 row-major [M,K] (activations, K contiguous)       -> TMA, 128B-swizzled smem tiles 128x64
+//   W : bf16 row-major [N,K] (nn.Linear / 1x1-conv weight)     -> TMA, 128B-swizzled smem tiles BNx64
+//   accumulators: fp32 in TMEM, two stages of BN columns so the epilogue of tile i overlaps the MMAs of tile i+1
+//
+// Warp roles (256 threads, 1 CTA per SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
+//   warp 0      TMA producer (one elected lane)
+//   warp 1      MMA issuer   (one elected lane issues tcgen05.mma; tcgen05.commit releases smem / publishes TMEM)
+//   warp 2      TMEM allocator / deallocator
+//   warps 4..7  epilogue: tcgen05.ld 32 lanes x 32 columns per warp, fused math, direct global stores
+//
+// Epilogues (reference call sites, /root/reference/tld/transformer_blocks.py):
+//   EPI_BF16            out_bf16 = acc                                   qkv_linear            (:58)
+//   EPI_BIAS_BF16       out_bf16 = acc + bias                            mlp.0 1x1 conv D->4D  (:95)
+//   EPI_BIAS_RESID_F32  x_f32   += acc + bias                            mlp.3 1x1 conv + "+x" (:104,:138)
+//   EPI_XATTN_RESID_F32 x_f32   += softmax2(q.k0, q.k1) . (v0, v1)       q_linear + 2-key SDPA + "+x" (:70-72,:137)
+//   EPI_F32             out_f32  = acc                                   kv_linear on cond tokens (:71)
+#pragma once
+#include "ptx.cuh"
+
+namespace tld {
+
+enum EpiMode : int {
+  EPI_BF16 = 0,
+  EPI_BIAS_BF16 = 1,
+  EPI_BIAS_RESID_F32 = 2,
+  EPI_XATTN_RESID_F32 = 3,
+  EPI_F32 = 4,
+};
+
+struct GemmEpi {
+  void* out;          // bf16* or float*, row-major, leading dimension ldo (elements)
+  int ldo;
+  const float* bias;  // [N] or nullptr
+  // cross-attention epilogue only
+  const float* kv0;   // cond token 0 (noise) K|V rows for this layer: K at [0,D), V at [D,2D)
+  const float* kv1;   // cond token 1 (label)
+  long long kv0_stride, kv1_stride;  // floats between consecutive rows
+  const int* step_ptr;  // if non-null: every sample uses kv0 row *step_ptr (hoisted per-step noise token)
+  int n_tok;          // tokens per sample (row -> sample = row / n_tok)
+  int embed_dim;      // D
+  float scale;        // 1/sqrt(head_dim)
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int GEMM_THREADS = 256;
+constexpr int UMMA_K = 16;
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int KV_BYTES = 2 * 4 * BN * 4;  // 2 samples x {k0,k1,v0,v1} x BN floats
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - KV_BYTES - 256 /*barriers*/;
+  static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
+  static constexpr int TOTAL = 1024 + STAGES * STAGE_BYTES + KV_BYTES + 256;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M,
+                    int N, int K, GemmEpi ep) {
+  using S = GemmSmem<BN>;
+  constexpr int STAGES = S::STAGES;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                 : (2 * BN <= 256) ? 256 : 512;
+  static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN must be 64..256, multiple of 64");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * S::A_BYTES;
+  float* smem_kv = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES + S::KV_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * GEMM_BM;
+        const int n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          tma_load_2d(smem_a + stage * S::A_BYTES, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
+          tma_load_2d(smem_b + stage * S::B_BYTES, &tmap_b, &full_bar[stage], kb * GEMM_BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t adesc = umma_smem_desc_sw128(smem_u32(smem_a + stage * S::A_BYTES), 16, 1024);
+          const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(smem_b + stage * S::B_BYTES), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / UMMA_K; ++k) {
+            // advance 32 B (16 bf16) along K inside the 128 B swizzle row: +2 in the (addr>>4) field
+            umma_ss_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);                      // smem slot free once these MMAs retire
+          if (kb == k_blocks - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;                 // == warp % 4: the TMEM lane quarter this warp may read
+    const int et = threadIdx.x - 128;        // 0..127 == accumulator row inside the tile
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile / n_tiles) * GEMM_BM;
+      const int n0 = (tile % n_tiles) * BN;
+      const int row = m0 + et;
+      const bool row_ok = row < M;
+
+      int sidx = 0;
+      if constexpr (EPI == EPI_XATTN_RESID_F32) {
+        // stage k0,k1,v0,v1 of the (at most two) samples this tile touches
+        const int b_first = m0 / ep.n_tok;
+        named_bar_sync(1, 128);  // previous tile's readers are done
+        for (int i = et; i < 2 * 4 * BN; i += 128) {
+          const int c = i % BN;
+          const int vec = (i / BN) & 3;       // 0:k0 1:k1 2:v0 3:v1
+          const int s = i / (4 * BN);
+          const int b = b_first + s;
+          float val = 0.f;
+          if ((long long)b * ep.n_tok < M && n0 + c < N) {
+            const int tok = vec & 1;
+            const long long r0 = ep.step_ptr ? (long long)(*ep.step_ptr) : (long long)b;
+            const float* src = tok == 0 ? ep.kv0 + r0 * ep.kv0_stride : ep.kv1 + (long long)b * ep.kv1_stride;
+            val = src[(vec >= 2 ? ep.embed_dim : 0) + n0 + c];
+          }
+          smem_kv[i] = val;
+        }
+        named_bar_sync(1, 128);
+        sidx = row_ok ? (row / ep.n_tok - b_first) : 0;
+      }
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + acc * BN;
+
+      if constexpr (EPI == EPI_XATTN_RESID_F32) {
+        float* xrow = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldo;
+        const float* kvb = smem_kv + sidx * 4 * BN;
+#pragma unroll 1
+        for (int hc = 0; hc < BN / 64; ++hc) {
+          uint32_t q[64];
+          tmem_ld_x32(taddr + hc * 64, *reinterpret_cast<uint32_t(*)[32]>(&q[0]));
+          tmem_ld_x32(taddr + hc * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&q[32]));
+          tmem_ld_wait();
+          const float4* k0 = reinterpret_cast<const float4*>(kvb + 0 * BN + hc * 64);
+          const float4* k1 = reinterpret_cast<const float4*>(kvb + 1 * BN + hc * 64);
+          const float4* v0 = reinterpret_cast<const float4*>(kvb + 2 * BN + hc * 64);
+          const float4* v1 = reinterpret_cast<const float4*>(kvb + 3 * BN + hc * 64);
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float4 a = k0[i], b = k1[i];
+            const float q0 = __uint_as_float(q[4 * i]), q1 = __uint_as_float(q[4 * i + 1]);
+            const float q2 = __uint_as_float(q[4 * i + 2]), q3 = __uint_as_float(q[4 * i + 3]);
+            s0 += q0 * a.x + q1 * a.y + q2 * a.z + q3 * a.w;
+            s1 += q0 * b.x + q1 * b.y + q2 * b.z + q3 * b.w;
+          }
+          s0 *= ep.scale;
+          s1 *= ep.scale;
+          const float mx = fmaxf(s0, s1);
+          const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx);
+          const float inv = 1.f / (e0 + e1);
+          const float p0 = e0 * inv, p1 = e1 * inv;
+          if (row_ok && n0 + hc * 64 < N) {
+            float4* xp = reinterpret_cast<float4*>(xrow + n0 + hc * 64);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float4 a = v0[i], b = v1[i];
+              float4 xv = xp[i];
+              xv.x += p0 * a.x + p1 * b.x;
+              xv.y += p0 * a.y + p1 * b.y;
+              xv.z += p0 * a.z + p1 * b.z;
+              xv.w += p0 * a.w + p1 * b.w;
+              xp[i] = xv;
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld_x32(taddr + ch * 32, r);
+          tmem_ld_wait();
+          const int col = n0 + ch * 32;
+          if (row_ok && col < N) {  // N is a multiple of 32 for every call site
+            if constexpr (EPI == EPI_BF16 || EPI == EPI_BIAS_BF16) {
+              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)row * ep.ldo + col;
+              uint4* o4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  f[j] = __uint_as_float(r[8 * i + j]);
+                  if constexpr (EPI == EPI_BIAS_BF16) f[j] += __ldg(ep.bias + col + 8 * i + j);
+                }
+                uint4 v;
+                v.x = pack_bf16x2(f[0], f[1]);
+                v.y = pack_bf16x2(f[2], f[3]);
+                v.z = pack_bf16x2(f[4], f[5]);
+                v.w = pack_bf16x2(f[6], f[7]);
+                o4[i] = v;
+              }
+            } else {
+              float* op = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldo + col;
+              float4* o4 = reinterpret_cast<float4*>(op);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 v;
+                v.x = __uint_as_float(r[4 * i]);
+                v.y = __uint_as_float(r[4 * i + 1]);
+                v.z = __uint_as_float(r[4 * i + 2]);
+                v.w = __uint_as_float(r[4 * i + 3]);
+                if constexpr (EPI == EPI_BIAS_RESID_F32) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + i);
+                  const float4 x = o4[i];
+                  v.x += b.x + x.x;
+                  v.y += b.y + x.y;
+                  v.z += b.z + x.z;
+                  v.w += b.w + x.w;
+                }
+                o4[i] = v;
+              }
+            }
+          }
+        }
+      }
+      // accumulator stage drained: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace tld
