@@ -66,16 +66,17 @@ TLD_API int tld_denoiser_missing_params(tld_denoiser* h);
 TLD_API int tld_denoiser_forward(tld_denoiser* h, const float* x, const float* noise_level, const float* label,
                          float* out, int batch, void* stream);
 
-/* ---- DiffusionGenerator.generate minus the VAE decode (tld/diffusion.py:29-89) --------------
+/* ---- DiffusionGenerator.generate minus the VAE decode (tld/diffusion.py:54-89) --------------
  * labels[num_imgs,text_emb] (the cond half; the zero uncond half is implicit, diffusion.py:61),
  * seeds[num_imgs,C,H,W] initial noise (diffusion.py:105-120), latent_out[num_imgs,C,H,W] = final x0_pred.
- * noise_levels: HOST pointer to n_levels floats or NULL for the default schedule
- * 1 - linspace(0,1,n_iter)^exponent (diffusion.py:50-52; [0] is forced to 0.99 either way).
+ * noise_levels: HOST pointer to the n_levels >= 2 noise levels the model is called at, i.e. the list built at
+ * diffusion.py:50-52 (the caller computes it: the sinusoidal embedding multiplies the level by up to 2*pi*1000,
+ * so the levels must be bit-identical to the reference's fp32 torch.arange/pow values; [0] is forced to 0.99
+ * here as well).  n_levels model calls are made (n_levels-1 updates + the final prediction, diffusion.py:66,85).
  * One diffusion step (2B-sample CFG forward + guidance + multistep update) is one CUDA-graph launch. */
 TLD_API int tld_sampler_generate(tld_denoiser* h, const float* labels, const float* seeds, float* latent_out,
-                         int num_imgs, int n_iter, float class_guidance, float exponent, float sharp_f,
-                         float bright_f, int use_ddpm_plus, const float* noise_levels, int n_levels,
-                         void* stream);
+                                 int num_imgs, const double* noise_levels, int n_levels, float class_guidance,
+                                 float sharp_f, float bright_f, int use_ddpm_plus, void* stream);
 /* Device time of the sampling loop of the last tld_sampler_generate call (ms, CUDA events) and number of
  * kernel launches (graph nodes x replays + prologue) it issued. */
 TLD_API int tld_sampler_last_stats(tld_denoiser* h, float* loop_ms, int64_t* kernel_launches);

@@ -388,29 +388,18 @@ int tld_denoiser_forward(tld_denoiser* h, const float* x, const float* noise_lev
 }
 
 int tld_sampler_generate(tld_denoiser* h, const float* labels, const float* seeds, float* latent_out, int num_imgs,
-                         int n_iter, float class_guidance, float exponent, float sharp_f, float bright_f,
-                         int use_ddpm_plus, const float* noise_levels, int n_levels, void* stream) {
-  TLD_CHECK(h && labels && seeds && latent_out, "tld_sampler_generate: null argument");
+                         const double* noise_levels, int n_levels, float class_guidance, float sharp_f,
+                         float bright_f, int use_ddpm_plus, void* stream) {
+  TLD_CHECK(h && labels && seeds && latent_out && noise_levels, "tld_sampler_generate: null argument");
   TLD_CHECK(num_imgs > 0, "tld_sampler_generate: num_imgs must be positive");
+  TLD_CHECK(n_levels >= 2, "tld_sampler_generate: need at least 2 noise levels");
   TLD_CHECK(tld_denoiser_missing_params(h) == 0, "tld_sampler_generate: parameters missing");
   TLD_CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t caller = reinterpret_cast<cudaStream_t>(stream);
   cudaStream_t st = h->own_stream;
 
-  // ---- schedule on the host (diffusion.py:50-57), python-float (double) arithmetic
-  std::vector<double> sig;
-  if (noise_levels) {
-    TLD_CHECK(n_levels >= 2, "tld_sampler_generate: need at least 2 noise levels");
-    for (int i = 0; i < n_levels; ++i) sig.push_back((double)noise_levels[i]);
-  } else {
-    TLD_CHECK(n_iter >= 2, "tld_sampler_generate: n_iter must be >= 2");
-    const double step = 1.0 / n_iter;
-    const int n = (int)ceil((1.0 - 0.0) / step);  // torch.arange(0, 1, 1/n_iter) length
-    for (int i = 0; i < n; ++i) {
-      const float v = (float)(0.0 + i * step);     // fp32 arange value
-      sig.push_back((double)(1.0f - powf(v, exponent)));
-    }
-  }
+  // ---- multistep coefficients on the host (diffusion.py:54-57,71-81), python-float (double) arithmetic
+  std::vector<double> sig(noise_levels, noise_levels + n_levels);
   sig[0] = 0.99;
   const int calls = (int)sig.size();
   std::vector<double> rs;

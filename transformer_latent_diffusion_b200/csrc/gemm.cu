@@ -26,16 +26,18 @@ static int resolve_encode() {
   return status;
 }
 
-// 2-D bf16 row-major tensor [rows, cols] (cols contiguous, leading dimension ld elements),
-// box = [box_rows, 64 cols], 128-byte swizzle, OOB reads zero-filled.
-static int make_tmap_bf16(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld,
-                          int box_rows) {
+// 2-D row-major tensor [rows, cols] (cols contiguous, leading dimension ld elements) of bf16 or fp32,
+// box = [box_rows, 128 bytes of columns], 128-byte swizzle, OOB reads zero-filled / OOB writes clipped.
+static int make_tmap_2d(CUtensorMap* m, const void* base, bool is_f32, long long rows, long long cols, long long ld,
+                        int box_rows) {
   if (resolve_encode()) return fail("cuTensorMapEncodeTiled entry point not available");
+  const int esz = is_f32 ? 4 : 2;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = g_encode(m, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                        const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed, CUresult=" + std::to_string((int)r));
@@ -43,10 +45,10 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, long long rows, long
 }
 
 template <int BN, int EPI>
-static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpi& ep,
-                    cudaStream_t st) {
+static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
+                    const GemmEpi& ep, cudaStream_t st) {
   auto kern = gemm_bf16_tn_kernel<BN, EPI>;
-  constexpr int smem = GemmSmem<BN>::TOTAL;
+  constexpr int smem = GemmSmem<BN, EPI>::TOTAL;
   static bool attr_set = false;
   if (!attr_set) {
     TLD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -54,20 +56,20 @@ static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, 
   }
   const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, GEMM_THREADS, smem, st>>>(ta, tb, M, N, K, ep);
+  kern<<<grid, GEMM_THREADS, smem, st>>>(ta, tb, tc, M, N, K, ep);
   TLD_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 template <int BN>
-static int launch_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpi& ep,
-                     cudaStream_t st) {
+static int launch_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
+                     const GemmEpi& ep, cudaStream_t st) {
   switch (epi) {
-    case EPI_BF16: return launch_t<BN, EPI_BF16>(ta, tb, M, N, K, ep, st);
-    case EPI_BIAS_BF16: return launch_t<BN, EPI_BIAS_BF16>(ta, tb, M, N, K, ep, st);
-    case EPI_BIAS_RESID_F32: return launch_t<BN, EPI_BIAS_RESID_F32>(ta, tb, M, N, K, ep, st);
-    case EPI_XATTN_RESID_F32: return launch_t<BN, EPI_XATTN_RESID_F32>(ta, tb, M, N, K, ep, st);
-    case EPI_F32: return launch_t<BN, EPI_F32>(ta, tb, M, N, K, ep, st);
+    case EPI_BF16: return launch_t<BN, EPI_BF16>(ta, tb, tc, M, N, K, ep, st);
+    case EPI_BIAS_BF16: return launch_t<BN, EPI_BIAS_BF16>(ta, tb, tc, M, N, K, ep, st);
+    case EPI_BIAS_RESID_F32: return launch_t<BN, EPI_BIAS_RESID_F32>(ta, tb, tc, M, N, K, ep, st);
+    case EPI_XATTN_RESID_F32: return launch_t<BN, EPI_XATTN_RESID_F32>(ta, tb, tc, M, N, K, ep, st);
+    case EPI_F32: return launch_t<BN, EPI_F32>(ta, tb, tc, M, N, K, ep, st);
   }
   return fail("launch_gemm: unknown epilogue " + std::to_string(epi));
 }
@@ -106,14 +108,17 @@ int launch_gemm(int epi, const bf16* A, int lda, const bf16* W, int ldw, int M, 
     TLD_CHECK(xa != nullptr, "launch_gemm: cross-attention epilogue needs XattnArgs");
     TLD_CHECK(N % 64 == 0 && xa->n_tok % 64 == 0, "launch_gemm: cross-attention epilogue needs N and n_tok multiples of 64");
   }
-  if (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_RESID_F32) TLD_CHECK(bias != nullptr, "launch_gemm: bias epilogue without bias");
+  if (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_RESID_F32)
+    TLD_CHECK(bias != nullptr && N % 64 == 0, "launch_gemm: bias epilogues need a bias and N % 64 == 0");
+  const bool out_f32 = !(epi == EPI_BF16 || epi == EPI_BIAS_BF16);
+  TLD_CHECK((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo * (out_f32 ? 4 : 2)) % 16 == 0,
+            "launch_gemm: output must be 16-byte aligned with a 16-byte multiple row pitch");
   const int bn = pick_bn(M, N);
-  CUtensorMap ta, tb;
-  if (make_tmap_bf16(&ta, A, M, K, lda, GEMM_BM)) return 1;
-  if (make_tmap_bf16(&tb, W, N, K, ldw, bn)) return 1;
+  CUtensorMap ta, tb, tc;
+  if (make_tmap_2d(&ta, A, false, M, K, lda, GEMM_BM)) return 1;
+  if (make_tmap_2d(&tb, W, false, N, K, ldw, bn)) return 1;
+  if (make_tmap_2d(&tc, out, out_f32, M, N, ldo, 32)) return 1;
   GemmEpi ep{};
-  ep.out = out;
-  ep.ldo = ldo;
   ep.bias = bias;
   ep.scale = 0.125f;  // 1/sqrt(64)
   if (xa) {
@@ -126,10 +131,10 @@ int launch_gemm(int epi, const bf16* A, int lda, const bf16* W, int ldw, int M, 
     ep.embed_dim = xa->embed_dim;
   }
   switch (bn) {
-    case 256: return launch_bn<256>(epi, ta, tb, M, N, K, ep, st);
-    case 192: return launch_bn<192>(epi, ta, tb, M, N, K, ep, st);
-    case 128: return launch_bn<128>(epi, ta, tb, M, N, K, ep, st);
-    case 64: return launch_bn<64>(epi, ta, tb, M, N, K, ep, st);
+    case 256: return launch_bn<256>(epi, ta, tb, tc, M, N, K, ep, st);
+    case 192: return launch_bn<192>(epi, ta, tb, tc, M, N, K, ep, st);
+    case 128: return launch_bn<128>(epi, ta, tb, tc, M, N, K, ep, st);
+    case 64: return launch_bn<64>(epi, ta, tb, tc, M, N, K, ep, st);
   }
   return fail("launch_gemm: no tile width for N=" + std::to_string(N));
 }

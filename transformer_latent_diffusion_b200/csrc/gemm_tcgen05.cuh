@@ -3,12 +3,16 @@
 //   A : bf16 row-major [M,K] (activations, K contiguous)       -> TMA, 128B-swizzled smem tiles 128x64
 //   W : bf16 row-major [N,K] (nn.Linear / 1x1-conv weight)     -> TMA, 128B-swizzled smem tiles BNx64
 //   accumulators: fp32 in TMEM, two stages of BN columns so the epilogue of tile i overlaps the MMAs of tile i+1
+//   C : written by TMA from 128B-swizzled shared-memory staging: plain tiled store for fresh outputs,
+//       TMA reduce-add (read-modify-write at L2, no x read through the SM) for the residual epilogues
 //
 // Warp roles (256 threads, 1 CTA per SM, grid = min(#tiles, #SMs), static round-robin tile schedule):
 //   warp 0      TMA producer (one elected lane)
 //   warp 1      MMA issuer   (one elected lane issues tcgen05.mma; tcgen05.commit releases smem / publishes TMEM)
 //   warp 2      TMEM allocator / deallocator
-//   warps 4..7  epilogue: tcgen05.ld 32 lanes x 32 columns per warp, fused math, direct global stores
+//   warps 4..7  epilogue: each warp owns 32 accumulator rows (its TMEM lane quarter): tcgen05.ld -> fused math
+//               -> its own [32 rows x 128 B] staging slab (double buffered) -> its own TMA store / reduce-add.
+//               No cross-warp synchronisation on the store path.
 //
 // Epilogues (reference call sites, /root/reference/tld/transformer_blocks.py):
 //   EPI_BF16            out_bf16 = acc                                   qkv_linear            (:58)
@@ -30,8 +34,6 @@ enum EpiMode : int {
 };
 
 struct GemmEpi {
-  void* out;          // bf16* or float*, row-major, leading dimension ldo (elements)
-  int ldo;
   const float* bias;  // [N] or nullptr
   // cross-attention epilogue only
   const float* kv0;   // cond token 0 (noise) K|V rows for this layer: K at [0,D), V at [D,2D)
@@ -47,34 +49,49 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int GEMM_THREADS = 256;
 constexpr int UMMA_K = 16;
+constexpr int STG_SLAB = 32 * 128;  // one epilogue warp's staging slab: 32 rows x 128 B
 
-template <int BN>
+template <int BN, int EPI>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int KV_BYTES = 2 * 4 * BN * 4;  // 2 samples x {k0,k1,v0,v1} x BN floats
-  static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - KV_BYTES - 256 /*barriers*/;
+  static constexpr int STG_BYTES = 4 * 2 * STG_SLAB;  // 4 warps x 2 buffers
+  static constexpr int KV_BYTES = (EPI == EPI_XATTN_RESID_F32) ? 2 * 4 * BN * 4 : 0;  // 2 samples x {k0,k1,v0,v1}
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - STG_BYTES - KV_BYTES - 256 /*barriers*/;
   static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
-  static constexpr int TOTAL = 1024 + STAGES * STAGE_BYTES + KV_BYTES + 256;
+  static constexpr int TOTAL = 1024 + STAGES * STAGE_BYTES + STG_BYTES + KV_BYTES + 256;
+  static_assert(STAGES >= 3, "not enough shared memory for a 3-stage pipeline");
 };
+
+// write this lane's 128-byte row into a 128B-swizzled [32 x 128 B] slab (conflict-free per quarter-warp)
+__device__ __forceinline__ void stage_row(uint8_t* slab, int lane, const uint32_t (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint4 q = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    *reinterpret_cast<uint4*>(slab + lane * 128 + ((j ^ (lane & 7)) << 4)) = q;
+  }
+}
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M,
-                    int N, int K, GemmEpi ep) {
-  using S = GemmSmem<BN>;
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K, GemmEpi ep) {
+  using S = GemmSmem<BN, EPI>;
   constexpr int STAGES = S::STAGES;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                  : (2 * BN <= 256) ? 256 : 512;
+  constexpr bool OUT_BF16 = (EPI == EPI_BF16 || EPI == EPI_BIAS_BF16);
+  constexpr bool REDUCE = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_XATTN_RESID_F32);
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN must be 64..256, multiple of 64");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * S::A_BYTES;
-  float* smem_kv = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES + S::KV_BYTES);
+  uint8_t* smem_stg = smem + STAGES * S::STAGE_BYTES;  // 1024-aligned: every stage size is a multiple of 1024
+  float* smem_kv = reinterpret_cast<float*>(smem_stg + S::STG_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + S::STG_BYTES + S::KV_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
@@ -91,6 +108,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_c);
   }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < STAGES; ++s) {
@@ -163,6 +181,26 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ===================== epilogue =====================
     const int ew = warp - 4;                 // == warp % 4: the TMEM lane quarter this warp may read
     const int et = threadIdx.x - 128;        // 0..127 == accumulator row inside the tile
+    uint8_t* my_stg = smem_stg + ew * 2 * STG_SLAB;
+    int buf = 0;
+    // push one staged [32 rows x 128 B] slab to global: plain store or reduce-add; ordering: lane 0 makes sure the
+    // slab it is about to hand out again has been read by the TMA unit before anyone overwrites it.
+    auto slab_acquire = [&]() -> uint8_t* {
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+      return my_stg + buf * STG_SLAB;
+    };
+    auto slab_release = [&](uint8_t* slab, int col, int row) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && row < M && col < N) {  // fully out-of-range slabs are skipped, partial ones are clipped by TMA
+        if constexpr (REDUCE) tma_reduce_add_2d(&tmap_c, slab, col, row);
+        else tma_store_2d(&tmap_c, slab, col, row);
+        bulk_commit();
+      }
+      buf ^= 1;
+    };
+
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -170,13 +208,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int m0 = (tile / n_tiles) * GEMM_BM;
       const int n0 = (tile % n_tiles) * BN;
       const int row = m0 + et;
-      const bool row_ok = row < M;
+      const int slab_row = m0 + ew * 32;
 
       int sidx = 0;
       if constexpr (EPI == EPI_XATTN_RESID_F32) {
         // stage k0,k1,v0,v1 of the (at most two) samples this tile touches
         const int b_first = m0 / ep.n_tok;
         named_bar_sync(1, 128);  // previous tile's readers are done
+        const long long r0s = ep.step_ptr ? (long long)(*ep.step_ptr) : -1;
         for (int i = et; i < 2 * 4 * BN; i += 128) {
           const int c = i % BN;
           const int vec = (i / BN) & 3;       // 0:k0 1:k1 2:v0 3:v1
@@ -184,15 +223,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const int b = b_first + s;
           float val = 0.f;
           if ((long long)b * ep.n_tok < M && n0 + c < N) {
-            const int tok = vec & 1;
-            const long long r0 = ep.step_ptr ? (long long)(*ep.step_ptr) : (long long)b;
-            const float* src = tok == 0 ? ep.kv0 + r0 * ep.kv0_stride : ep.kv1 + (long long)b * ep.kv1_stride;
-            val = src[(vec >= 2 ? ep.embed_dim : 0) + n0 + c];
+            const long long r0 = r0s >= 0 ? r0s : (long long)b;
+            const float* src = (vec & 1) == 0 ? ep.kv0 + r0 * ep.kv0_stride : ep.kv1 + (long long)b * ep.kv1_stride;
+            val = __ldg(src + (vec >= 2 ? ep.embed_dim : 0) + n0 + c);
           }
           smem_kv[i] = val;
         }
         named_bar_sync(1, 128);
-        sidx = row_ok ? (row / ep.n_tok - b_first) : 0;
+        sidx = row < M ? (row / ep.n_tok - b_first) : 0;
       }
 
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -200,46 +238,77 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + acc * BN;
 
       if constexpr (EPI == EPI_XATTN_RESID_F32) {
-        float* xrow = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldo;
         const float* kvb = smem_kv + sidx * 4 * BN;
 #pragma unroll 1
         for (int hc = 0; hc < BN / 64; ++hc) {
-          uint32_t q[64];
-          tmem_ld_x32(taddr + hc * 64, *reinterpret_cast<uint32_t(*)[32]>(&q[0]));
-          tmem_ld_x32(taddr + hc * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&q[32]));
+          uint32_t qa[32], qb[32];
+          tmem_ld_x32(taddr + hc * 64, qa);
+          tmem_ld_x32(taddr + hc * 64 + 32, qb);
           tmem_ld_wait();
           const float4* k0 = reinterpret_cast<const float4*>(kvb + 0 * BN + hc * 64);
           const float4* k1 = reinterpret_cast<const float4*>(kvb + 1 * BN + hc * 64);
           const float4* v0 = reinterpret_cast<const float4*>(kvb + 2 * BN + hc * 64);
           const float4* v1 = reinterpret_cast<const float4*>(kvb + 3 * BN + hc * 64);
-          float s0 = 0.f, s1 = 0.f;
+          float s0a = 0.f, s0b = 0.f, s1a = 0.f, s1b = 0.f;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float4 a = k0[i], b = k1[i];
-            const float q0 = __uint_as_float(q[4 * i]), q1 = __uint_as_float(q[4 * i + 1]);
-            const float q2 = __uint_as_float(q[4 * i + 2]), q3 = __uint_as_float(q[4 * i + 3]);
-            s0 += q0 * a.x + q1 * a.y + q2 * a.z + q3 * a.w;
-            s1 += q0 * b.x + q1 * b.y + q2 * b.z + q3 * b.w;
+          for (int i = 0; i < 8; ++i) {
+            const float4 a = k0[i], b = k1[i], c = k0[8 + i], d = k1[8 + i];
+            const float x0 = __uint_as_float(qa[4 * i]), x1 = __uint_as_float(qa[4 * i + 1]);
+            const float x2 = __uint_as_float(qa[4 * i + 2]), x3 = __uint_as_float(qa[4 * i + 3]);
+            const float y0 = __uint_as_float(qb[4 * i]), y1 = __uint_as_float(qb[4 * i + 1]);
+            const float y2 = __uint_as_float(qb[4 * i + 2]), y3 = __uint_as_float(qb[4 * i + 3]);
+            s0a += x0 * a.x + x1 * a.y + x2 * a.z + x3 * a.w;
+            s1a += x0 * b.x + x1 * b.y + x2 * b.z + x3 * b.w;
+            s0b += y0 * c.x + y1 * c.y + y2 * c.z + y3 * c.w;
+            s1b += y0 * d.x + y1 * d.y + y2 * d.z + y3 * d.w;
           }
-          s0 *= ep.scale;
-          s1 *= ep.scale;
+          const float s0 = (s0a + s0b) * ep.scale, s1 = (s1a + s1b) * ep.scale;
           const float mx = fmaxf(s0, s1);
           const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx);
           const float inv = 1.f / (e0 + e1);
           const float p0 = e0 * inv, p1 = e1 * inv;
-          if (row_ok && n0 + hc * 64 < N) {
-            float4* xp = reinterpret_cast<float4*>(xrow + n0 + hc * 64);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float4 a = v0[i], b = v1[i];
-              float4 xv = xp[i];
-              xv.x += p0 * a.x + p1 * b.x;
-              xv.y += p0 * a.y + p1 * b.y;
-              xv.z += p0 * a.z + p1 * b.z;
-              xv.w += p0 * a.w + p1 * b.w;
-              xp[i] = xv;
+          for (int half = 0; half < 2; ++half) {
+            uint32_t o[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 a = v0[half * 8 + i], b = v1[half * 8 + i];
+              o[4 * i] = __float_as_uint(p0 * a.x + p1 * b.x);
+              o[4 * i + 1] = __float_as_uint(p0 * a.y + p1 * b.y);
+              o[4 * i + 2] = __float_as_uint(p0 * a.z + p1 * b.z);
+              o[4 * i + 3] = __float_as_uint(p0 * a.w + p1 * b.w);
             }
+            uint8_t* slab = slab_acquire();
+            stage_row(slab, lane, o);
+            slab_release(slab, n0 + hc * 64 + half * 32, slab_row);
           }
+        }
+      } else if constexpr (OUT_BF16) {
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 64; ++ch) {
+          uint32_t ra[32], rb[32];
+          tmem_ld_x32(taddr + ch * 64, ra);
+          tmem_ld_x32(taddr + ch * 64 + 32, rb);
+          tmem_ld_wait();
+          const int col = n0 + ch * 64;
+          uint32_t o[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float f0 = __uint_as_float(ra[2 * i]), f1 = __uint_as_float(ra[2 * i + 1]);
+            float g0 = __uint_as_float(rb[2 * i]), g1 = __uint_as_float(rb[2 * i + 1]);
+            if constexpr (EPI == EPI_BIAS_BF16) {
+              if (col + 63 < N) {
+                const float2 b0 = __ldg(reinterpret_cast<const float2*>(ep.bias + col) + i);
+                const float2 b1 = __ldg(reinterpret_cast<const float2*>(ep.bias + col + 32) + i);
+                f0 += b0.x; f1 += b0.y; g0 += b1.x; g1 += b1.y;
+              }
+            }
+            o[i] = pack_bf16x2(f0, f1);
+            o[16 + i] = pack_bf16x2(g0, g1);
+          }
+          uint8_t* slab = slab_acquire();
+          stage_row(slab, lane, o);
+          slab_release(slab, col, slab_row);
         }
       } else {
 #pragma unroll 1
@@ -248,47 +317,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tmem_ld_x32(taddr + ch * 32, r);
           tmem_ld_wait();
           const int col = n0 + ch * 32;
-          if (row_ok && col < N) {  // N is a multiple of 32 for every call site
-            if constexpr (EPI == EPI_BF16 || EPI == EPI_BIAS_BF16) {
-              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)row * ep.ldo + col;
-              uint4* o4 = reinterpret_cast<uint4*>(op);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float f[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  f[j] = __uint_as_float(r[8 * i + j]);
-                  if constexpr (EPI == EPI_BIAS_BF16) f[j] += __ldg(ep.bias + col + 8 * i + j);
-                }
-                uint4 v;
-                v.x = pack_bf16x2(f[0], f[1]);
-                v.y = pack_bf16x2(f[2], f[3]);
-                v.z = pack_bf16x2(f[4], f[5]);
-                v.w = pack_bf16x2(f[6], f[7]);
-                o4[i] = v;
-              }
-            } else {
-              float* op = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldo + col;
-              float4* o4 = reinterpret_cast<float4*>(op);
+          if constexpr (EPI == EPI_BIAS_RESID_F32) {
+            if (col + 31 < N) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                float4 v;
-                v.x = __uint_as_float(r[4 * i]);
-                v.y = __uint_as_float(r[4 * i + 1]);
-                v.z = __uint_as_float(r[4 * i + 2]);
-                v.w = __uint_as_float(r[4 * i + 3]);
-                if constexpr (EPI == EPI_BIAS_RESID_F32) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + i);
-                  const float4 x = o4[i];
-                  v.x += b.x + x.x;
-                  v.y += b.y + x.y;
-                  v.z += b.z + x.z;
-                  v.w += b.w + x.w;
-                }
-                o4[i] = v;
+                const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + i);
+                r[4 * i] = __float_as_uint(__uint_as_float(r[4 * i]) + b.x);
+                r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + b.y);
+                r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + b.z);
+                r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + b.w);
               }
             }
           }
+          uint8_t* slab = slab_acquire();
+          stage_row(slab, lane, r);
+          slab_release(slab, col, slab_row);
         }
       }
       // accumulator stage drained: hand it back to the MMA warp
@@ -296,6 +339,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (lane == 0) bulk_wait<0>();  // all stores/reductions of this warp complete before the CTA may exit
   }
 
   tc_fence_before();

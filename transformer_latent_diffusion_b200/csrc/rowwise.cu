@@ -279,88 +279,102 @@ int launch_cond_label(const float* label, int R, int R_real, int Te, int D, cons
 
 // --------------------------------------------------------------------------------------------
 // Depthwise 3x3 ('same', zero pad) + bias + exact GELU over the token grid (transformer_blocks.py:96-103).
-// Layout: h, g bf16 [B, grid, grid, C] (token-major == NHWC).  One thread owns 8 channels of one grid row and
-// slides along x with a 3x3 register window: 3 new 16-byte loads per 8 outputs; weights stay in registers.
+// Layout: h, g bf16 [B, grid, grid, C] (token-major == NHWC).  One thread owns 4 channels of one grid row and
+// slides along x with a 3x3 fp32 register window (each loaded value is unpacked once): 3 new 8-byte loads per
+// 4 outputs; the 36 weights stay in registers.  The kernel is ALU-bound (9 FMA + GELU per element at
+// 100 M elements per layer), so erf uses Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below the bf16
+// rounding of the output) on the MUFU ex2/rcp units instead of the ~25-instruction libdevice erff.
 // --------------------------------------------------------------------------------------------
-__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+__device__ __forceinline__ float gelu_fast_erf(float v) {
+  const float z = fabsf(v) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = __expf(-z * z);
+  const float erf_abs = fmaf(-p * t, e, 1.0f);  // erf(|v|/sqrt2)
+  const float hv = 0.5f * v;
+  return fmaf(hv, copysignf(erf_abs, v), hv);
+}
+
+__device__ __forceinline__ void unpack4(const uint2& v, float (&f)[4]) {
   f[0] = __uint_as_float(v.x << 16);
   f[1] = __uint_as_float(v.x & 0xffff0000u);
   f[2] = __uint_as_float(v.y << 16);
   f[3] = __uint_as_float(v.y & 0xffff0000u);
-  f[4] = __uint_as_float(v.z << 16);
-  f[5] = __uint_as_float(v.z & 0xffff0000u);
-  f[6] = __uint_as_float(v.w << 16);
-  f[7] = __uint_as_float(v.w & 0xffff0000u);
 }
 
 __global__ void __launch_bounds__(256) dwconv_gelu_kernel(const bf16* __restrict__ h, const float* __restrict__ w9,
                                                           const float* __restrict__ bias, bf16* __restrict__ g, int B,
                                                           int grid, int C) {
-  const int c8n = C / 8;
+  const int c4n = C / 4;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)B * grid * c8n) return;
-  const int c8 = int(idx % c8n);
-  const int gy = int((idx / c8n) % grid);
-  const int b = int(idx / ((long long)c8n * grid));
-  const int c0 = c8 * 8;
-  float w[9][8], bs[8];
+  if (idx >= (long long)B * grid * c4n) return;
+  const int c4 = int(idx % c4n);
+  const int gy = int((idx / c4n) % grid);
+  const int b = int(idx / ((long long)c4n * grid));
+  const int c0 = c4 * 4;
+  float w[9][4], bs[4];
 #pragma unroll
   for (int tp = 0; tp < 9; ++tp) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(w9 + (size_t)tp * C + c0));
-    const float4 bq = __ldg(reinterpret_cast<const float4*>(w9 + (size_t)tp * C + c0) + 1);
     w[tp][0] = a.x; w[tp][1] = a.y; w[tp][2] = a.z; w[tp][3] = a.w;
-    w[tp][4] = bq.x; w[tp][5] = bq.y; w[tp][6] = bq.z; w[tp][7] = bq.w;
   }
   {
     const float4 a = __ldg(reinterpret_cast<const float4*>(bias + c0));
-    const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + c0) + 1);
-    bs[0] = a.x; bs[1] = a.y; bs[2] = a.z; bs[3] = a.w; bs[4] = bq.x; bs[5] = bq.y; bs[6] = bq.z; bs[7] = bq.w;
+    bs[0] = a.x; bs[1] = a.y; bs[2] = a.z; bs[3] = a.w;
   }
-  const size_t img_base = (size_t)b * grid * grid * C;
-  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-  auto ld = [&](int yy, int xx) -> uint4 {
-    if (yy < 0 || yy >= grid || xx < 0 || xx >= grid) return zero;
-    return *reinterpret_cast<const uint4*>(h + img_base + ((size_t)yy * grid + xx) * C + c0);
-  };
-  uint4 win[3][3];  // [dy][dx] window centred on (gy, x)
-#pragma unroll
-  for (int dy = 0; dy < 3; ++dy) {
-    win[dy][0] = zero;
-    win[dy][1] = ld(gy + dy - 1, 0);
-    win[dy][2] = ld(gy + dy - 1, 1);
-  }
-  for (int xq = 0; xq < grid; ++xq) {
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bs[j];
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        float f[8];
-        unpack8(win[dy][dx], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += w[dy * 3 + dx][j] * f[j];
-      }
-    uint4 o;
-    o.x = pack_bf16x2_dev(gelu_erf(acc[0]), gelu_erf(acc[1]));
-    o.y = pack_bf16x2_dev(gelu_erf(acc[2]), gelu_erf(acc[3]));
-    o.z = pack_bf16x2_dev(gelu_erf(acc[4]), gelu_erf(acc[5]));
-    o.w = pack_bf16x2_dev(gelu_erf(acc[6]), gelu_erf(acc[7]));
-    *reinterpret_cast<uint4*>(g + img_base + ((size_t)gy * grid + xq) * C + c0) = o;
+  const size_t img_base = (size_t)b * grid * grid * C + c0;
+  const bool up = gy > 0, dn = gy + 1 < grid;
+  // col[k][dy][ch]: three window columns in rotating roles
+  float col[3][3][4];
+  auto load_col = [&](float (&dst)[3][4], int xx) {
+    const bool okx = xx >= 0 && xx < grid;
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
-      win[dy][0] = win[dy][1];
-      win[dy][1] = win[dy][2];
-      win[dy][2] = ld(gy + dy - 1, xq + 2);
+      const bool ok = okx && (dy == 1 || (dy == 0 ? up : dn));
+      uint2 v = make_uint2(0u, 0u);
+      if (ok) v = *reinterpret_cast<const uint2*>(h + img_base + ((size_t)(gy + dy - 1) * grid + xx) * C);
+      unpack4(v, dst[dy]);
+    }
+  };
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) col[0][dy][j] = 0.f;
+  load_col(col[1], 0);
+  load_col(col[2], 1);
+  for (int x0 = 0; x0 < grid; x0 += 3) {
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int xq = x0 + u;
+      if (xq < grid) {
+        // window columns: left = col[u%3], centre = col[(u+1)%3], right = col[(u+2)%3]
+        float acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = bs[j];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = fmaf(w[dy * 3 + dx][j], col[(u + dx) % 3][dy][j], acc[j]);
+        uint2 o;
+        o.x = pack_bf16x2_dev(gelu_fast_erf(acc[0]), gelu_fast_erf(acc[1]));
+        o.y = pack_bf16x2_dev(gelu_fast_erf(acc[2]), gelu_fast_erf(acc[3]));
+        *reinterpret_cast<uint2*>(g + img_base + ((size_t)gy * grid + xq) * C) = o;
+        load_col(col[u % 3], xq + 2);  // the old left column becomes the next right column
+      }
     }
   }
 }
 
 int launch_dwconv_gelu(const bf16* h, const float* w9, const float* bias, bf16* g, int B, int grid, int C,
                        cudaStream_t st) {
-  TLD_CHECK(C % 8 == 0, "dwconv: channel count must be a multiple of 8");
-  const long long threads = (long long)B * grid * (C / 8);
+  TLD_CHECK(C % 4 == 0, "dwconv: channel count must be a multiple of 4");
+  TLD_CHECK(grid >= 2, "dwconv: token grid must be at least 2x2");
+  const long long threads = (long long)B * grid * (C / 4);
   const int blocks = int((threads + 255) / 256);
   dwconv_gelu_kernel<<<blocks, 256, 0, st>>>(h, w9, bias, g, B, grid, C);
   TLD_CUDA_OK(cudaGetLastError());

@@ -92,12 +92,12 @@ class DiffusionGenerator:
         lab = labels.to(device=dev, dtype=torch.float32).contiguous()
         x0 = x_t.to(device=dev, dtype=torch.float32).contiguous()
         out = torch.empty_like(x0)
-        levels = (C.c_float * len(sig))(*sig)
+        levels = (C.c_double * len(sig))(*sig)  # python floats, exactly as the reference loop sees them
         with torch.cuda.device(dev):
             _lib.check(_lib.load().tld_sampler_generate(
-                h, _lib.ptr(lab), _lib.ptr(x0), _lib.ptr(out), num_imgs, len(sig), float(class_guidance),
-                float(exponent), float(sharp_f), float(bright_f), int(bool(use_ddpm_plus)), levels, len(sig),
-                _lib.current_stream_ptr(dev)), "tld_sampler_generate")
+                h, _lib.ptr(lab), _lib.ptr(x0), _lib.ptr(out), num_imgs, levels, len(sig), float(class_guidance),
+                float(sharp_f), float(bright_f), int(bool(use_ddpm_plus)), _lib.current_stream_ptr(dev)),
+                "tld_sampler_generate")
         return out.to(self.model_dtype)
 
     def last_stats(self) -> "tuple[float, int]":
