@@ -1,0 +1,310 @@
+#!/usr/bin/env python3
+"""bench.py — 256-px images/sec with 35-step CFG sampling (BASELINE.json metric, configs[1]).
+
+One "step" = one full pass of the hot path over one batch: `DiffusionGenerator.generate` semantics for B images
+(35 model calls on the 2B-sample CFG batch through the CUDA-graph sampler) + the VAE decode of the B latents.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                 # this repo (libtld_b200, sm_100a)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus 8 --steps 5 --warmup 3                     # batch-sharded, one process per GPU, no collective
+    python bench.py --impl reference --steps 2 --warmup 1         # reference algorithm on the host cores
+
+Prints ONE JSON line (rank 0).  `value` = whole-job images/s with inputs resident in HBM; `e2e` = the same metric
+through the public API with pinned HOST inputs (H2D of labels+noise, D2H of the decoded images inside the timed
+region).  `roofline` is the dominant kernel (tcgen05 GEMM, MLP up-projection shape) timed alone with CUDA events;
+`cpu_baseline` is the oracle port (oracle/tld_oracle.py, the reference algorithm in torch fp32) on the box's host
+cores over a bounded sample.  Weights are random-init (no checkpoint offline), data synthetic.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+IMG, D, L, N_ITER, GUIDANCE = 32, 768, 12, 35, 6.0  # BASELINE configs[1]: 100M denoiser, 4x32x32 latent
+
+
+def fwd_flops_per_sample(img=IMG, d=D, layers=L) -> float:
+    n = (img // 2) ** 2
+    blk = 24 * n * d * d + 4 * n * n * d + 80 * n * d + 8 * d * d
+    eh = 2 * n * 16 * 16 + 4 * n * 16 * d + 2 * (256 * d + d * d) + 2 * 768 * d
+    return float(layers * blk + eh)
+
+
+# ------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ reference / cpu arm
+def cpu_generation(num_imgs: int, n_iter: int, threads: int) -> float:
+    """One bounded pass of the reference algorithm on the host: oracle sampler + oracle VAE decode. Returns seconds."""
+    from oracle import tld_oracle as O
+    from oracle import vae_oracle as V
+    from transformer_latent_diffusion_b200.vae import AutoencoderKLDecoder
+
+    torch.set_num_threads(threads)
+    cfg = O.OracleCfg(image_size=IMG, embed_dim=D, n_layers=L)
+    if not hasattr(cpu_generation, "_state"):
+        torch.manual_seed(0)
+        vae_sd = {k: v.detach() for k, v in AutoencoderKLDecoder().state_dict().items()}
+        cpu_generation._state = (O.synth_state_dict(cfg, 0), vae_sd)
+    sd, vae_sd = cpu_generation._state
+    g = torch.Generator().manual_seed(1)
+    labels = torch.randn(num_imgs, 768, generator=g)
+    seeds = torch.randn(num_imgs, 4, IMG, IMG, generator=g)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        lat = O.generate_latents(sd, cfg, labels, seeds, n_iter=n_iter, class_guidance=GUIDANCE, exponent=1,
+                                 sharp_f=0, bright_f=0, use_ddpm_plus=True)
+        V.decode(vae_sd, lat * 8)
+    return time.perf_counter() - t0
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # the CPU arm runs on rank 0 only
+    threads = os.cpu_count() or 1
+    sample_imgs = args.cpu_images
+    for _ in range(args.warmup):
+        cpu_generation(sample_imgs, N_ITER, threads)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_generation(sample_imgs, N_ITER, threads)
+    value = sample_imgs * args.steps / t
+    sample = f"{sample_imgs} image(s) x {N_ITER} CFG steps + VAE decode per step, fp32, {threads} torch threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "images_per_sec_256px_35step_cfg", "value": value, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "100M denoiser 256px sampling: 4x32x32 latent, 35-step CFG (oracle port on host CPU)",
+                   "images_per_step": sample_imgs, "n_iter": N_ITER, "class_guidance": GUIDANCE},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def time_dominant_gemm(lib, peaks) -> dict:
+    """MLP up-projection GEMM (T=32768, N=3072, K=768, +bias -> bf16) timed alone: CUDA events on the launch
+    stream, operands rotated through buffers larger than L2 between launches."""
+    M, N, K = 128 * (IMG // 2) ** 2, 4 * D, D
+    nbuf = 4  # 4 x (50 MB A + 200 MB C) > 126 MB L2
+    A = [torch.randn(M, K, device="cuda").bfloat16() for _ in range(nbuf)]
+    W = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    C = [torch.empty(M, N, device="cuda", dtype=torch.bfloat16) for _ in range(nbuf)]
+    st = torch.cuda.current_stream().cuda_stream
+    L_ = lib.load()
+    for i in range(3):
+        lib.check(L_.tld_op_gemm(1, lib.ptr(A[i % nbuf]), lib.ptr(W), M, N, K, lib.ptr(C[i % nbuf]), lib.ptr(bias), st), "gemm")
+    reps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(reps):
+        lib.check(L_.tld_op_gemm(1, lib.ptr(A[i % nbuf]), lib.ptr(W), M, N, K, lib.ptr(C[i % nbuf]), lib.ptr(bias), st), "gemm")
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * M * N * K
+    achieved = flops / (ms * 1e-3) / 1e12
+    peak = peaks.get("bf16_tflops")
+    src = "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+    if not peak:
+        peak, src = 1590.0, "fallback (B200_PROFILING.md)"
+    del A, C
+    return {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel<256,EPI_BIAS_BF16> (mlp.0 up-projection, M=32768 N=3072 K=768)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": src,
+            "ms_per_launch": ms, "flops_per_launch": flops,
+            "traffic": 200.9e6,  # dram read+write per launch from profiles/r01_gemm_ncu.txt (ncu --set full)
+            "method": "CUDA events around 20 back-to-back launches on the launch stream, 4 rotating operand sets (>L2)"}
+
+
+def run_b200(args) -> None:
+    from transformer_latent_diffusion_b200 import _lib
+    from transformer_latent_diffusion_b200.denoiser import Denoiser
+    from transformer_latent_diffusion_b200.diffusion import DiffusionGenerator
+    from transformer_latent_diffusion_b200.vae import AutoencoderKLDecoder
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch  # images per GPU per step (weak scaling: fixed per-GPU work)
+    torch.manual_seed(0)
+    model = Denoiser(IMG, 256, 2, D, 0, L).to(dev).eval()
+    vae = AutoencoderKLDecoder().to(device=dev, dtype=torch.bfloat16).eval()
+    gen = DiffusionGenerator(model, vae, dev, torch.float32)
+    g = torch.Generator().manual_seed(1 + rank)
+    labels_h = torch.randn(B, 768, generator=g).pin_memory()
+    seeds_h = torch.randn(B, 4, IMG, IMG, generator=torch.Generator().manual_seed(11 + rank)).pin_memory()
+    labels_d, seeds_d = labels_h.to(dev), seeds_h.to(dev)
+    out_h = torch.empty(B, 3, 8 * IMG, 8 * IMG).pin_memory()
+
+    def step_resident():
+        lat = gen.generate_latents(labels_d, n_iter=N_ITER, num_imgs=B, class_guidance=GUIDANCE, img_size=IMG,
+                                   sharp_f=0, bright_f=0, exponent=1, seeds=seeds_d)
+        return vae.decode(lat * 8)[0]
+
+    def step_e2e():  # public API call with host tensors; the image comes back to (pinned) host memory
+        lab = labels_h.to(dev, non_blocking=True)
+        sd = seeds_h.to(dev, non_blocking=True)
+        lat = gen.generate_latents(lab, n_iter=N_ITER, num_imgs=B, class_guidance=GUIDANCE, img_size=IMG,
+                                   sharp_f=0, bright_f=0, exponent=1, seeds=sd)
+        out_h.copy_(vae.decode(lat * 8)[0], non_blocking=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    # denoiser-only loop time of one step (device events inside the library)
+    step_resident()
+    torch.cuda.synchronize()
+    loop_ms, launches = gen.last_stats()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_total = timed(step_resident, args.steps)
+    clocks = sampler.stop()
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    value = world * B * args.steps / (ms_total * 1e-3)
+    e2e_val = world * B * args.steps / (ms_e2e * 1e-3)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    roof = time_dominant_gemm(_lib, peaks)
+    flops_img = 2 * N_ITER * fwd_flops_per_sample() + AutoencoderKLDecoder.flops_per_image(IMG)
+    sustained = peaks.get("bf16_tflops_sustained") or 1400.0
+    line = {
+        "metric": "images_per_sec_256px_35step_cfg", "value": value, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "100M denoiser 256px sampling: 4x32x32 latent, 35-step CFG, batch=64 per GPU + VAE decode",
+                   "images_per_gpu_per_step": B, "n_iter": N_ITER, "class_guidance": GUIDANCE, "cfg_batch": 2 * B,
+                   "parallelism": f"batch-sharded x{world}, no collective", "weights": "random-init",
+                   "l2": "inputs larger than L2: 202 MB bf16 weights + >1 GB activations per step vs 126 MB L2",
+                   "denoiser": "libtld_b200 (hand-written sm_100a, CUDA-graph step)",
+                   "vae_decode": "torch/cuDNN bf16 library kernels (round 1; not yet hand-written)"},
+        "denoiser_step_ms": loop_ms / N_ITER, "denoiser_only_images_per_s_per_gpu": B / (loop_ms * 1e-3),
+        "flops_per_image": flops_img,
+        "model_tflops_whole_step": flops_img * value / 1e12,
+        "frac_of_sustained_bf16_peak_whole_step": flops_img * value / 1e12 / (sustained * world),
+        "e2e": {"value": e2e_val, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": labels_h.numel() * 4 + seeds_h.numel() * 4, "d2h_bytes_per_step": out_h.numel() * 4},
+        "gpu_launches": int(launches) * args.steps,
+        "clocks": clocks,
+        "roofline": roof,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n = args.cpu_images
+        t = cpu_generation(n, N_ITER, threads)
+        line["cpu_baseline"] = {"value": n / t, "unit": "images/s", "cores": threads, "kind": "port",
+                                "sample": f"{n} image(s) x {N_ITER} CFG steps + VAE decode, oracle port fp32, {threads} torch threads, {t:.1f} s"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--cpu-images", type=int, default=1, help="images per CPU step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

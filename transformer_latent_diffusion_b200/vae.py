@@ -1,0 +1,185 @@
+"""VAE decoder (row A13 of SURVEY.md §8a): the SDXL ``AutoencoderKL`` decoder the reference calls once per
+generation (``self.vae.decode(z)[0]``, tld/diffusion.py:91; ``madebyollin/sdxl-vae-fp16-fix``, tld/configs.py:42).
+
+The reference takes this module from the third-party ``diffusers`` package, which (like its weights) is not
+available offline, so PARITY IS UNPINNED for this row: the architecture below follows the published
+diffusers/SDXL-VAE structure with diffusers-compatible ``state_dict`` keys (``post_quant_conv``,
+``decoder.conv_in``, ``decoder.mid_block.*``, ``decoder.up_blocks.*``, ``decoder.conv_norm_out``,
+``decoder.conv_out``) so the real checkpoint loads when it is available, and is checked against the independent
+fp32 restatement in ``oracle/vae_oracle.py`` with random weights.
+
+ROUND-1 STATUS: the convolutions/GroupNorm here run on PyTorch's library kernels (cuDNN implicit-GEMM, ATen
+GroupNorm) in bf16/channels-last -- this is the one place on the north-star path that is not yet hand-written
+sm_100a code (see DESIGN.md "VAE decode").  bench.py reports the denoiser-only number next to the end-to-end one.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+GN_GROUPS = 32
+GN_EPS = 1e-6
+BLOCK_OUT = (128, 256, 512, 512)  # sdxl-vae config.json block_out_channels
+LAYERS_PER_BLOCK = 2
+LATENT_CH = 4
+
+
+def vae_param_layout(latent_ch: int = LATENT_CH, block_out=BLOCK_OUT) -> "Dict[str, tuple]":
+    """Ordered {key: shape} of the decoder half of diffusers.AutoencoderKL (decoder + post_quant_conv)."""
+    lay: Dict[str, tuple] = {}
+
+    def conv(name, cout, cin, k):
+        lay[name + ".weight"] = (cout, cin, k, k)
+        lay[name + ".bias"] = (cout,)
+
+    def norm(name, c):
+        lay[name + ".weight"] = (c,)
+        lay[name + ".bias"] = (c,)
+
+    def resnet(name, cin, cout):
+        norm(name + ".norm1", cin)
+        conv(name + ".conv1", cout, cin, 3)
+        norm(name + ".norm2", cout)
+        conv(name + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(name + ".conv_shortcut", cout, cin, 1)
+
+    top = block_out[-1]
+    conv("post_quant_conv", latent_ch, latent_ch, 1)
+    conv("decoder.conv_in", top, latent_ch, 3)
+    resnet("decoder.mid_block.resnets.0", top, top)
+    a = "decoder.mid_block.attentions.0"
+    norm(a + ".group_norm", top)
+    for p in ("to_q", "to_k", "to_v", "to_out.0"):
+        lay[f"{a}.{p}.weight"] = (top, top)
+        lay[f"{a}.{p}.bias"] = (top,)
+    resnet("decoder.mid_block.resnets.1", top, top)
+    rev = list(reversed(block_out))
+    prev = rev[0]
+    for i, cout in enumerate(rev):
+        for j in range(LAYERS_PER_BLOCK + 1):
+            resnet(f"decoder.up_blocks.{i}.resnets.{j}", prev if j == 0 else cout, cout)
+        if i != len(rev) - 1:
+            conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", cout, cout, 3)
+        prev = cout
+    norm("decoder.conv_norm_out", block_out[0])
+    conv("decoder.conv_out", 3, block_out[0], 3)
+    return lay
+
+
+class _Node(nn.Module):
+    pass
+
+
+def _attach(root: nn.Module, dotted: str, value: torch.Tensor) -> None:
+    *path, leaf = dotted.split(".")
+    mod = root
+    for name in path:
+        if name not in mod._modules:
+            mod.add_module(name, _Node())
+        mod = mod._modules[name]
+    mod.register_parameter(leaf, nn.Parameter(value))
+
+
+class AutoencoderKLDecoder(nn.Module):
+    """``decode(z) -> (image,)`` with the SDXL-VAE decoder topology; z is the latent as the reference passes it
+    (already multiplied by ``scale_factor``, tld/diffusion.py:91)."""
+
+    def __init__(self, latent_ch: int = LATENT_CH, block_out: Tuple[int, ...] = BLOCK_OUT, chunk: int = 16):
+        super().__init__()
+        self.latent_ch, self.block_out, self.chunk = latent_ch, tuple(block_out), chunk
+        self._layout = vae_param_layout(latent_ch, block_out)
+        for key, shape in self._layout.items():
+            if key.endswith("weight") and len(shape) == 1:
+                t = torch.ones(shape)
+            elif key.endswith("bias"):
+                t = torch.zeros(shape)
+            else:
+                fan_in = int(math.prod(shape[1:]))
+                t = torch.empty(shape).uniform_(-1.0 / math.sqrt(fan_in), 1.0 / math.sqrt(fan_in))
+            _attach(self, key, t)
+
+    def _p(self, key: str) -> torch.Tensor:
+        mod = self
+        *path, leaf = key.split(".")
+        for name in path:
+            mod = mod._modules[name]
+        return mod._parameters[leaf]
+
+    # -- building blocks ---------------------------------------------------------------------------------------
+    def _conv(self, x, name, pad):
+        return F.conv2d(x, self._p(name + ".weight"), self._p(name + ".bias"), padding=pad)
+
+    def _gn_silu(self, x, name):
+        return F.silu(F.group_norm(x, GN_GROUPS, self._p(name + ".weight"), self._p(name + ".bias"), GN_EPS))
+
+    def _resnet(self, x, name):
+        h = self._conv(self._gn_silu(x, name + ".norm1"), name + ".conv1", 1)
+        h = self._conv(self._gn_silu(h, name + ".norm2"), name + ".conv2", 1)
+        if (name + ".conv_shortcut.weight") in self._layout:
+            x = self._conv(x, name + ".conv_shortcut", 0)
+        return x + h
+
+    def _mid_attention(self, x, name):
+        B, Cc, H, W = x.shape
+        h = F.group_norm(x, GN_GROUPS, self._p(name + ".group_norm.weight"), self._p(name + ".group_norm.bias"), GN_EPS)
+        t = h.permute(0, 2, 3, 1).reshape(B, H * W, Cc)
+        q = F.linear(t, self._p(name + ".to_q.weight"), self._p(name + ".to_q.bias"))
+        k = F.linear(t, self._p(name + ".to_k.weight"), self._p(name + ".to_k.bias"))
+        v = F.linear(t, self._p(name + ".to_v.weight"), self._p(name + ".to_v.bias"))
+        o = F.scaled_dot_product_attention(q.unsqueeze(1), k.unsqueeze(1), v.unsqueeze(1)).squeeze(1)  # 1 head
+        o = F.linear(o, self._p(name + ".to_out.0.weight"), self._p(name + ".to_out.0.bias"))
+        return x + o.reshape(B, H, W, Cc).permute(0, 3, 1, 2)
+
+    def _decode_chunk(self, z):
+        x = self._conv(z, "post_quant_conv", 0)
+        x = self._conv(x, "decoder.conv_in", 1)
+        x = self._resnet(x, "decoder.mid_block.resnets.0")
+        x = self._mid_attention(x, "decoder.mid_block.attentions.0")
+        x = self._resnet(x, "decoder.mid_block.resnets.1")
+        n_up = len(self.block_out)
+        for i in range(n_up):
+            for j in range(LAYERS_PER_BLOCK + 1):
+                x = self._resnet(x, f"decoder.up_blocks.{i}.resnets.{j}")
+            if i != n_up - 1:
+                x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+                x = self._conv(x, f"decoder.up_blocks.{i}.upsamplers.0.conv", 1)
+        x = self._gn_silu(x, "decoder.conv_norm_out")
+        return self._conv(x, "decoder.conv_out", 1)
+
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor):
+        """z [B,4,h,w] -> (image [B,3,8h,8w],) in z's dtype; processed in chunks of ``self.chunk`` images."""
+        w = self._p("decoder.conv_in.weight")
+        zz = z.to(device=w.device, dtype=w.dtype)
+        if zz.is_cuda:
+            zz = zz.contiguous(memory_format=torch.channels_last)
+        outs = [self._decode_chunk(zz[i:i + self.chunk]) for i in range(0, zz.shape[0], self.chunk)]
+        return (torch.cat(outs).to(z.dtype),)
+
+    @staticmethod
+    def flops_per_image(latent_hw: int, block_out=BLOCK_OUT, latent_ch: int = LATENT_CH) -> float:
+        """Algorithmic FLOPs of one decode (2*MACs of every conv/linear + the mid attention)."""
+        top = block_out[-1]
+        hw = latent_hw * latent_hw
+
+        def res(n, cin, cout):
+            return 2.0 * n * (cin * cout * 9 + cout * cout * 9 + (cin * cout if cin != cout else 0))
+
+        f = 2.0 * hw * (latent_ch * latent_ch + latent_ch * top * 9)
+        f += 2 * res(hw, top, top) + 4 * 2.0 * hw * top * top + 4.0 * hw * hw * top
+        rev = list(reversed(block_out))
+        prev, n = rev[0], hw
+        for i, cout in enumerate(rev):
+            for j in range(LAYERS_PER_BLOCK + 1):
+                f += res(n, prev if j == 0 else cout, cout)
+            if i != len(rev) - 1:
+                n *= 4
+                f += 2.0 * n * cout * cout * 9
+            prev = cout
+        f += 2.0 * n * block_out[0] * 3 * 9
+        return f
