@@ -48,6 +48,9 @@ typedef struct tld_config {
 
 TLD_API const char* tld_last_error(void);
 TLD_API int tld_version(void);
+/* Process-wide tuning switches (tests / experiments): "gemm_ctas" = 0 auto | 1 single-CTA tiles | 2 CTA-pair
+ * (cta_group::2) tiles;  "attention_impl" = 0 auto | 1 mma.sync kernel | 2 tcgen05 kernel. */
+TLD_API int tld_set_option(const char* key, int value);
 
 /* ---- lifetime --------------------------------------------------------------------------------
  * Replaces Denoiser.__init__ + .to(device) (tld/denoiser.py:86-114, tld/diffusion.py:145-155). */
@@ -92,7 +95,9 @@ TLD_API int tld_op_gemm_xattn(const uint16_t* A, const uint16_t* Wq, int M, int 
                       const float* kv1, int n_tok, void* stream);
 TLD_API int tld_op_layernorm(const float* x, const float* gamma, const float* beta, uint16_t* y, int rows, int D,
                      void* stream);
-TLD_API int tld_op_self_attention(const uint16_t* qkv, float* x, int batch, int n_tok, int D, void* stream);
+/* x[T,D] += softmax(q k^T/8) v per (sample, head) from qkv[T,3D]; impl 0 = auto, 1 = mma.sync kernel,
+ * 2 = tcgen05 kernel (needs n_tok % 128 == 0) */
+TLD_API int tld_op_self_attention(const uint16_t* qkv, float* x, int batch, int n_tok, int D, int impl, void* stream);
 TLD_API int tld_op_dwconv_gelu(const uint16_t* h, const float* w9, const float* bias, uint16_t* g, int batch, int grid,
                        int channels, void* stream);
 

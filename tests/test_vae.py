@@ -53,5 +53,9 @@ def test_decode_gpu_bf16_matches_oracle():
     m = _small()
     z = torch.randn(3, 4, 16, 16)
     ref = V.decode({k: v.detach() for k, v in m.state_dict().items()}, z)
-    (img,) = m.cuda().to(torch.bfloat16).decode(z.cuda())
-    assert img.dtype == torch.float32 and rel_fro(img, ref) < 3e-2
+    torch.backends.cudnn.allow_tf32 = False
+    (img32,) = m.cuda().decode(z.cuda())
+    assert rel_fro(img32, ref) < 1e-4
+    # bf16 weights AND activations through ~35 conv/GroupNorm layers with random weights: a few percent
+    (img,) = m.to(torch.bfloat16).decode(z.cuda())
+    assert img.dtype == torch.float32 and rel_fro(img, ref) < 8e-2

@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out && rm -f gpurun_out/summary.txt
+run() { name=$1; shift; timeout -k 10 "$@" > gpurun_out/$name.log 2>&1; echo "$name exit=$?" >> gpurun_out/summary.txt; tail -3 gpurun_out/$name.log >> gpurun_out/summary.txt; }
+run t_attn 240 python -m pytest tests/test_ops_gpu.py -q -k "attention" --no-header -p no:cacheprovider
+run t_cta2 300 python -m pytest tests/test_ops_gpu.py -q -k "cta2" --no-header -p no:cacheprovider
+run t_all 600 python -m pytest tests -q -m gpu --no-header -p no:cacheprovider
+run time_auto 300 python tools/time_forward.py --batch 64 --reps 3
+run time_cta1 300 python tools/time_forward.py --batch 64 --reps 3 --gemm-ctas 1 --forward-only
+run time_attn1 300 python tools/time_forward.py --batch 64 --reps 3 --attn-impl 1 --forward-only
+timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_fwd.csv \
+  python tools/time_forward.py --batch 64 --reps 1 --forward-only > gpurun_out/ncu_fwd.log 2>&1
+timeout -k 10 600 python bench.py --steps 2 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
+echo "bench exit=$?" >> gpurun_out/summary.txt
+cat gpurun_out/summary.txt; cat gpurun_out/bench.json | cut -c1-2500

@@ -24,7 +24,12 @@ def main():
     ap.add_argument("--steps", type=int, default=35)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--forward-only", action="store_true")
+    ap.add_argument("--gemm-ctas", type=int, default=0)
+    ap.add_argument("--attn-impl", type=int, default=0)
     a = ap.parse_args()
+    from transformer_latent_diffusion_b200 import _lib
+    _lib.check(_lib.load().tld_set_option(b"gemm_ctas", a.gemm_ctas), "opt")
+    _lib.check(_lib.load().tld_set_option(b"attention_impl", a.attn_impl), "opt")
     torch.manual_seed(0)
     m = Denoiser(a.img, 256, 2, 768, 0, 12).cuda().eval()
     B2 = 2 * a.batch

@@ -30,6 +30,7 @@ class TldConfig(C.Structure):
 PROTOTYPES = {
     "tld_last_error": (C.c_char_p, []),
     "tld_version": (C.c_int, []),
+    "tld_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "tld_denoiser_create": (C.c_int, [C.POINTER(TldConfig), C.c_int, C.POINTER(C.c_void_p)]),
     "tld_denoiser_destroy": (None, [C.c_void_p]),
     "tld_denoiser_set_param": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
@@ -45,7 +46,7 @@ PROTOTYPES = {
     "tld_op_gemm_xattn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_void_p]),
     "tld_op_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
-    "tld_op_self_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "tld_op_self_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tld_op_dwconv_gelu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p]),
 }

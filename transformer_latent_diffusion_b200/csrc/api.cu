@@ -235,6 +235,8 @@ static int ensure_cond(tld_denoiser* h, int rows) {
   return 0;
 }
 
+static int g_attention_impl = 0;  // tld_set_option("attention_impl", ...)
+
 // The L decoder blocks + output projection on the tokens already in h->x_res (transformer_blocks.py:135-139).
 static int run_blocks(tld_denoiser* h, int batch, const float* kv0, long long kv0_stride, const float* kv1,
                       long long kv1_stride, const int* step_ptr, float* out, cudaStream_t st) {
@@ -245,7 +247,7 @@ static int run_blocks(tld_denoiser* h, int batch, const float* kv0, long long kv
     // x = SelfAttention(LN1(x)) + x
     if (launch_layernorm_bf16(h->x_res, ly.ln1w, ly.ln1b, h->xn, T, D, st)) return 1;
     if (launch_gemm(EPI_BF16, h->xn, D, ly.wqkv, D, T, 3 * D, D, h->qkv, 3 * D, nullptr, nullptr, st)) return 1;
-    if (launch_self_attention(h->qkv, h->x_res, batch, N, D, st)) return 1;
+    if (launch_self_attention(h->qkv, h->x_res, batch, N, D, st, g_attention_impl)) return 1;
     // x = CrossAttention(LN2(x), y) + x
     if (launch_layernorm_bf16(h->x_res, ly.ln2w, ly.ln2b, h->xn, T, D, st)) return 1;
     XattnArgs xa;
@@ -276,6 +278,22 @@ extern "C" {
 
 const char* tld_last_error(void) { return tld::last_error(); }
 int tld_version(void) { return 1; }
+
+int tld_set_option(const char* key, int value) {
+  TLD_CHECK(key != nullptr, "tld_set_option: null key");
+  const std::string k(key);
+  if (k == "gemm_ctas") {
+    TLD_CHECK(value >= 0 && value <= 2, "gemm_ctas must be 0, 1 or 2");
+    set_gemm_ctas(value);
+    return 0;
+  }
+  if (k == "attention_impl") {
+    TLD_CHECK(value >= 0 && value <= 2, "attention_impl must be 0, 1 or 2");
+    g_attention_impl = value;
+    return 0;
+  }
+  return fail("tld_set_option: unknown key " + k);
+}
 
 int tld_denoiser_create(const tld_config* cfg, int device, tld_denoiser** out) {
   TLD_CHECK(cfg && out, "tld_denoiser_create: null argument");
@@ -546,9 +564,10 @@ int tld_op_layernorm(const float* x, const float* gamma, const float* beta, uint
                                reinterpret_cast<cudaStream_t>(stream));
 }
 
-int tld_op_self_attention(const uint16_t* qkv, float* x, int batch, int n_tok, int D, void* stream) {
+int tld_op_self_attention(const uint16_t* qkv, float* x, int batch, int n_tok, int D, int impl, void* stream) {
+  TLD_CHECK(impl >= 0 && impl <= 2, "tld_op_self_attention: impl must be 0 (auto), 1 (mma.sync) or 2 (tcgen05)");
   return launch_self_attention(reinterpret_cast<const bf16*>(qkv), x, batch, n_tok, D,
-                               reinterpret_cast<cudaStream_t>(stream));
+                               reinterpret_cast<cudaStream_t>(stream), impl);
 }
 
 int tld_op_dwconv_gelu(const uint16_t* hsrc, const float* w9, const float* bias, uint16_t* g, int batch, int grid,

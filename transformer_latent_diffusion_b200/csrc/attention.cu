@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(ATT_THREADS) self_attention_kernel(const bf16*
   }
 }
 
-int launch_self_attention(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st) {
+int launch_self_attention_mma(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st) {
   TLD_CHECK(D % 64 == 0, "self_attention: embed_dim must be a multiple of 64");
   TLD_CHECK(n_tok % 64 == 0, "self_attention: tokens per sample must be a multiple of 64");
   TLD_CHECK(B <= 65535, "self_attention: batch too large for gridDim.z");
@@ -210,6 +210,11 @@ int launch_self_attention(const bf16* qkv, float* x, int B, int n_tok, int D, cu
   self_attention_kernel<<<grid, ATT_THREADS, 0, st>>>(qkv, x, n_tok, D);
   TLD_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+int launch_self_attention(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st, int impl) {
+  if (impl == 2 || (impl == 0 && n_tok % 128 == 0)) return launch_self_attention_tc(qkv, x, B, n_tok, D, st);
+  return launch_self_attention_mma(qkv, x, B, n_tok, D, st);
 }
 
 }  // namespace tld

@@ -1,0 +1,237 @@
+// tcgen05 flash-attention for head_dim 64, non-causal, fused with the residual add (no out-proj in the reference):
+//     x[t, h*64:(h+1)*64] += softmax(q k^T / 8) v            (transformer_blocks.py:31-48,57-59,136)
+//
+// CTA = 128 query rows of one (sample, head); keys are consumed in chunks of 128:
+//     S[128x128] = Q K_c^T          tcgen05.mma, A = Q (smem, K-major), B = K_c (smem, K-major), D in TMEM cols [0,128)
+//     P = exp2(S*c - m*c)           128 softmax threads, one row each: tcgen05.ld -> running max/sum in registers,
+//                                   P written as bf16 into 128B-swizzled K-major smem tiles
+//     O_c[128x64] = P V_c           tcgen05.mma, A = P (smem, K-major), B = V_c (smem, MN-major: hd contiguous),
+//                                   D in TMEM cols [128,192); added into the register accumulator with the online-
+//                                   softmax correction, so TMEM never needs rescaling
+// Output: O/l -> swizzled fp32 staging -> TMA reduce-add into the fp32 residual stream.
+// Warps 0..3: softmax + epilogue (TMEM lane quarter = warp id).  Warp 4: TMEM alloc, TMA loads, MMA issue.
+// 80 KB smem + 256 TMEM columns per CTA -> two CTAs per SM overlap each other's MMA and MUFU phases.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace tld {
+
+constexpr int TA_BQ = 128, TA_BK = 128, TA_HD = 64, TA_THREADS = 160;
+constexpr int TA_Q_BYTES = TA_BQ * TA_HD * 2;   // 16 KB
+constexpr int TA_K_BYTES = TA_BK * TA_HD * 2;   // 16 KB
+constexpr int TA_P_BYTES = TA_BQ * TA_BK * 2;   // 32 KB (two [128 x 64] K-major sub-tiles); reused as fp32 staging
+constexpr int TA_SMEM = 1024 + TA_Q_BYTES + 2 * TA_K_BYTES + TA_P_BYTES + 128;
+
+__global__ void __launch_bounds__(TA_THREADS, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_x, int n_tok,
+                    int D) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + TA_Q_BYTES;
+  uint8_t* sV = sK + TA_K_BYTES;
+  uint8_t* sP = sV + TA_K_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + TA_P_BYTES);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_k = bars + 1;
+  uint64_t* bar_v = bars + 2;
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_p = bars + 4;
+  uint64_t* bar_o = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int n_chunks = n_tok / TA_BK;
+  const int row_q = b * n_tok + qt * TA_BQ;   // first query row (token index) of this CTA
+  const int row_k = b * n_tok;                // first key row of this sample
+  const int col_q = head * TA_HD, col_k = D + head * TA_HD, col_v = 2 * D + head * TA_HD;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmap_qkv);
+      tma_prefetch_desc(&tmap_x);
+      mbar_init(bar_q, 1);
+      mbar_init(bar_k, 1);
+      mbar_init(bar_v, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 128);
+      mbar_init(bar_o, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base;         // S: columns [0,128)
+  const uint32_t tmem_o = tmem_base + 128;   // O chunk: columns [128,192)
+
+  if (warp == 4) {
+    // ===================== control: TMA loads + MMA issue (one lane) =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(TA_BQ, TA_BK, 0, 0);   // S = Q K^T : both K-major
+      constexpr uint32_t idesc_o = umma_idesc_bf16(TA_BQ, TA_HD, 0, 1);   // O = P V   : B (V) is MN-major
+      mbar_expect_tx(bar_q, TA_Q_BYTES);
+      tma_load_2d(sQ, &tmap_qkv, bar_q, col_q, row_q);
+      mbar_expect_tx(bar_k, TA_K_BYTES);
+      tma_load_2d(sK, &tmap_qkv, bar_k, col_k, row_k);
+      mbar_expect_tx(bar_v, TA_K_BYTES);
+      tma_load_2d(sV, &tmap_qkv, bar_v, col_v, row_k);
+      mbar_wait(bar_q, 0);
+      for (int c = 0; c < n_chunks; ++c) {
+        const uint32_t ph = c & 1;
+        mbar_wait(bar_k, ph);
+        tc_fence_after();
+        {
+          const uint64_t adesc = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+          const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sK), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < TA_HD / 16; ++k) umma_ss_f16(tmem_s, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
+          umma_commit(bar_s);
+        }
+        mbar_wait(bar_s, ph);  // S complete -> the K buffer is free for the next chunk
+        if (c + 1 < n_chunks) {
+          mbar_expect_tx(bar_k, TA_K_BYTES);
+          tma_load_2d(sK, &tmap_qkv, bar_k, col_k, row_k + (c + 1) * TA_BK);
+        }
+        mbar_wait(bar_p, ph);  // P written (and S fully read) by all 128 softmax threads
+        mbar_wait(bar_v, ph);
+        tc_fence_after();
+        {
+#pragma unroll
+          for (int kk = 0; kk < TA_BK / 16; ++kk) {
+            // A: P sub-tile kk/4 ([128 x 64] K-major), 32 B per k-step inside the swizzle row
+            const uint64_t adesc = umma_smem_desc_sw128(smem_u32(sP + (kk >> 2) * (TA_BQ * 128)), 16, 1024) + 2 * (kk & 3);
+            // B: V rows kk*16.. (keys) x 64 hd, MN-major: 8-key groups are 1024 B apart (SBO)
+            const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sV + kk * 16 * 128), TA_BK * 128, 1024);
+            umma_ss_f16(tmem_o, adesc, bdesc, idesc_o, kk != 0);
+          }
+          umma_commit(bar_o);
+        }
+        mbar_wait(bar_o, ph);  // O chunk complete -> V and P buffers are free
+        if (c + 1 < n_chunks) {
+          mbar_expect_tx(bar_v, TA_K_BYTES);
+          tma_load_2d(sV, &tmap_qkv, bar_v, col_v, row_k + (c + 1) * TA_BK);
+        }
+      }
+    }
+  } else {
+    // ===================== softmax + epilogue: thread = one query row =====================
+    const int r = threadIdx.x;  // 0..127
+    const uint32_t lane_base = uint32_t(warp * 32) << 16;
+    const float sl2 = 0.125f * 1.4426950408889634f;
+    float o[TA_HD];
+#pragma unroll
+    for (int i = 0; i < TA_HD; ++i) o[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int c = 0; c < n_chunks; ++c) {
+      const uint32_t ph = c & 1;
+      mbar_wait(bar_s, ph);
+      tc_fence_after();
+      // pass 1: row maximum of this chunk
+      float mx = m_run;
+#pragma unroll 1
+      for (int j = 0; j < TA_BK / 32; ++j) {
+        uint32_t s[32];
+        tmem_ld_x32(tmem_s + lane_base + j * 32, s);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+      }
+      const float corr = exp2f((m_run - mx) * sl2);
+      const float mb = mx * sl2;
+      m_run = mx;
+      // pass 2: P = exp2(s*c - m*c) -> bf16 -> swizzled K-major smem; row sum
+      float rs = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < TA_BK / 32; ++j) {
+        uint32_t s[32];
+        tmem_ld_x32(tmem_s + lane_base + j * 32, s);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * i]), sl2, -mb));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), sl2, -mb));
+          rs += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        uint8_t* sub = sP + (j >> 1) * (TA_BQ * 128) + r * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = (j & 1) * 4 + q;
+          *reinterpret_cast<uint4*>(sub + ((chunk ^ (r & 7)) << 4)) =
+              make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+      }
+      l_run = l_run * corr + rs;
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(bar_p);
+#pragma unroll
+      for (int i = 0; i < TA_HD; ++i) o[i] *= corr;
+      mbar_wait(bar_o, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < TA_HD / 32; ++j) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_o + lane_base + j * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[j * 32 + i] += __uint_as_float(v[i]);
+      }
+      tc_fence_before();
+    }
+    // epilogue: x += O / l  via this warp's own staging slabs (aliasing the now dead P buffer) + TMA reduce-add
+    const float inv = 1.f / l_run;
+    uint8_t* slab = sP + warp * (2 * 32 * 128);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint8_t* sl = slab + half * (32 * 128);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 q4 = make_float4(o[half * 32 + 4 * j] * inv, o[half * 32 + 4 * j + 1] * inv,
+                                o[half * 32 + 4 * j + 2] * inv, o[half * 32 + 4 * j + 3] * inv);
+        *reinterpret_cast<float4*>(sl + lane * 128 + ((j ^ (lane & 7)) << 4)) = q4;
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_reduce_add_2d(&tmap_x, slab, col_q, row_q + warp * 32);
+      tma_reduce_add_2d(&tmap_x, slab + 32 * 128, col_q + 32, row_q + warp * 32);
+      bulk_commit();
+      bulk_wait<0>();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+int launch_self_attention_tc(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st) {
+  TLD_CHECK(D % 64 == 0 && n_tok % 128 == 0, "attention_tc: needs embed_dim % 64 == 0 and tokens per sample % 128 == 0");
+  TLD_CHECK(B <= 65535, "attention_tc: batch too large for gridDim.z");
+  static bool attr_set = false;
+  if (!attr_set) {
+    TLD_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
+    attr_set = true;
+  }
+  const long long T = (long long)B * n_tok;
+  CUtensorMap tq, tx;
+  if (make_tmap_2d(&tq, qkv, false, T, 3LL * D, 3LL * D, 128)) return 1;
+  if (make_tmap_2d(&tx, x, true, T, D, D, 32)) return 1;
+  dim3 grid(n_tok / TA_BQ, D / 64, B);
+  attention_tc_kernel<<<grid, TA_THREADS, TA_SMEM, st>>>(tq, tx, n_tok, D);
+  TLD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace tld

@@ -1,5 +1,6 @@
 // Internal launcher declarations shared by the translation units of libtld_b200.so.
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -92,8 +93,17 @@ int launch_cfg_update(const float* model_out, float* x_t, float* x0_prev, float*
                       const int* step_ptr, int B, int C, int hw, cudaStream_t st);
 int launch_advance_step(int* step_ptr, cudaStream_t st);
 
-// ---------------------------------------------------------------- attention.cu
+void set_gemm_ctas(int v);  // 0 auto, 1 single-CTA tiles, 2 CTA-pair tiles (experiments / tests)
+
+// 2-D row-major TMA descriptor (bf16 or fp32), box = [box_rows, 128 bytes], 128B swizzle (gemm.cu)
+int make_tmap_2d(CUtensorMap* m, const void* base, bool is_f32, long long rows, long long cols, long long ld,
+                 int box_rows);
+
+// ---------------------------------------------------------------- attention.cu / attention_tc.cu
 // x[T,D] fp32 += softmax(q k^T / 8) v per (sample, head); qkv bf16 [T,3D] (q | k | v), head_dim 64
-int launch_self_attention(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st);
+// impl: 0 = auto (tcgen05 when n_tok % 128 == 0, else mma.sync), 1 = mma.sync kernel, 2 = tcgen05 kernel
+int launch_self_attention(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st, int impl = 0);
+int launch_self_attention_mma(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st);
+int launch_self_attention_tc(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st);
 
 }  // namespace tld

@@ -28,7 +28,7 @@ static int resolve_encode() {
 
 // 2-D row-major tensor [rows, cols] (cols contiguous, leading dimension ld elements) of bf16 or fp32,
 // box = [box_rows, 128 bytes of columns], 128-byte swizzle, OOB reads zero-filled / OOB writes clipped.
-static int make_tmap_2d(CUtensorMap* m, const void* base, bool is_f32, long long rows, long long cols, long long ld,
+int make_tmap_2d(CUtensorMap* m, const void* base, bool is_f32, long long rows, long long cols, long long ld,
                         int box_rows) {
   if (resolve_encode()) return fail("cuTensorMapEncodeTiled entry point not available");
   const int esz = is_f32 ? 4 : 2;
@@ -44,42 +44,57 @@ static int make_tmap_2d(CUtensorMap* m, const void* base, bool is_f32, long long
   return 0;
 }
 
-template <int BN, int EPI>
+static int g_gemm_ctas = 0;  // 0 = auto, 1 = single-CTA tiles, 2 = CTA-pair (cta_group::2) tiles
+void set_gemm_ctas(int v) { g_gemm_ctas = v; }
+
+template <int BN, int EPI, int CTAS>
 static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
                     const GemmEpi& ep, cudaStream_t st) {
-  auto kern = gemm_bf16_tn_kernel<BN, EPI>;
-  constexpr int smem = GemmSmem<BN, EPI>::TOTAL;
+  auto kern = gemm_bf16_tn_kernel<BN, EPI, CTAS>;
+  constexpr int smem = GemmSmem<BN, EPI, CTAS>::TOTAL;
   static bool attr_set = false;
   if (!attr_set) {
     TLD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, GEMM_THREADS, smem, st>>>(ta, tb, tc, M, N, K, ep);
-  TLD_CUDA_OK(cudaGetLastError());
+  const int tiles = ((M + GEMM_BM * CTAS - 1) / (GEMM_BM * CTAS)) * ((N + BN - 1) / BN);
+  const int slots = sm_count() / CTAS;  // CTAs (or CTA pairs) resident at once
+  const int grid = (tiles < slots ? tiles : slots) * CTAS;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TLD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, M, N, K, ep));
   return 0;
 }
 
-template <int BN>
+template <int BN, int CTAS>
 static int launch_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
                      const GemmEpi& ep, cudaStream_t st) {
   switch (epi) {
-    case EPI_BF16: return launch_t<BN, EPI_BF16>(ta, tb, tc, M, N, K, ep, st);
-    case EPI_BIAS_BF16: return launch_t<BN, EPI_BIAS_BF16>(ta, tb, tc, M, N, K, ep, st);
-    case EPI_BIAS_RESID_F32: return launch_t<BN, EPI_BIAS_RESID_F32>(ta, tb, tc, M, N, K, ep, st);
-    case EPI_XATTN_RESID_F32: return launch_t<BN, EPI_XATTN_RESID_F32>(ta, tb, tc, M, N, K, ep, st);
-    case EPI_F32: return launch_t<BN, EPI_F32>(ta, tb, tc, M, N, K, ep, st);
+    case EPI_BF16: return launch_t<BN, EPI_BF16, CTAS>(ta, tb, tc, M, N, K, ep, st);
+    case EPI_BIAS_BF16: return launch_t<BN, EPI_BIAS_BF16, CTAS>(ta, tb, tc, M, N, K, ep, st);
+    case EPI_BIAS_RESID_F32: return launch_t<BN, EPI_BIAS_RESID_F32, CTAS>(ta, tb, tc, M, N, K, ep, st);
+    case EPI_XATTN_RESID_F32: return launch_t<BN, EPI_XATTN_RESID_F32, CTAS>(ta, tb, tc, M, N, K, ep, st);
+    case EPI_F32: return launch_t<BN, EPI_F32, CTAS>(ta, tb, tc, M, N, K, ep, st);
   }
   return fail("launch_gemm: unknown epilogue " + std::to_string(epi));
 }
 
 // Tile width: the widest BN in {256,192,128,64} that divides N, preferring the one with the least
 // wave-quantisation loss on the persistent grid (ties -> wider tile, fewer A re-reads).
-static int pick_bn(int M, int N) {
+static int pick_bn(int M, int N, int ctas) {
   const int cands[4] = {256, 192, 128, 64};
-  const int sms = sm_count();
-  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  const int sms = sm_count() / ctas;
+  const int m_tiles = (M + GEMM_BM * ctas - 1) / (GEMM_BM * ctas);
   int best = 0;
   double best_cost = 1e30;
   for (int bn : cands) {
@@ -113,10 +128,12 @@ int launch_gemm(int epi, const bf16* A, int lda, const bf16* W, int ldw, int M, 
   const bool out_f32 = !(epi == EPI_BF16 || epi == EPI_BIAS_BF16);
   TLD_CHECK((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo * (out_f32 ? 4 : 2)) % 16 == 0,
             "launch_gemm: output must be 16-byte aligned with a 16-byte multiple row pitch");
-  const int bn = pick_bn(M, N);
+  // CTA pairs pay off once there are enough 256-row tiles to fill the 74 SM pairs
+  const int ctas = g_gemm_ctas ? g_gemm_ctas : (M >= 4096 ? 2 : 1);
+  const int bn = pick_bn(M, N, ctas);
   CUtensorMap ta, tb, tc;
   if (make_tmap_2d(&ta, A, false, M, K, lda, GEMM_BM)) return 1;
-  if (make_tmap_2d(&tb, W, false, N, K, ldw, bn)) return 1;
+  if (make_tmap_2d(&tb, W, false, N, K, ldw, bn / ctas)) return 1;
   if (make_tmap_2d(&tc, out, out_f32, M, N, ldo, 32)) return 1;
   GemmEpi ep{};
   ep.bias = bias;
@@ -130,11 +147,19 @@ int launch_gemm(int epi, const bf16* A, int lda, const bf16* W, int ldw, int M, 
     ep.n_tok = xa->n_tok;
     ep.embed_dim = xa->embed_dim;
   }
+  if (ctas == 2) {
+    switch (bn) {
+      case 256: return launch_bn<256, 2>(epi, ta, tb, tc, M, N, K, ep, st);
+      case 192: return launch_bn<192, 2>(epi, ta, tb, tc, M, N, K, ep, st);
+      case 128: return launch_bn<128, 2>(epi, ta, tb, tc, M, N, K, ep, st);
+      case 64: return launch_bn<64, 2>(epi, ta, tb, tc, M, N, K, ep, st);
+    }
+  }
   switch (bn) {
-    case 256: return launch_bn<256>(epi, ta, tb, tc, M, N, K, ep, st);
-    case 192: return launch_bn<192>(epi, ta, tb, tc, M, N, K, ep, st);
-    case 128: return launch_bn<128>(epi, ta, tb, tc, M, N, K, ep, st);
-    case 64: return launch_bn<64>(epi, ta, tb, tc, M, N, K, ep, st);
+    case 256: return launch_bn<256, 1>(epi, ta, tb, tc, M, N, K, ep, st);
+    case 192: return launch_bn<192, 1>(epi, ta, tb, tc, M, N, K, ep, st);
+    case 128: return launch_bn<128, 1>(epi, ta, tb, tc, M, N, K, ep, st);
+    case 64: return launch_bn<64, 1>(epi, ta, tb, tc, M, N, K, ep, st);
   }
   return fail("launch_gemm: no tile width for N=" + std::to_string(N));
 }

@@ -14,6 +14,13 @@
 //               -> its own [32 rows x 128 B] staging slab (double buffered) -> its own TMA store / reduce-add.
 //               No cross-warp synchronisation on the store path.
 //
+// CTAS = 2 (cta_group::2): two CTAs of a cluster (an SM pair) share one 256 x BN tile.  Each CTA stages its own
+// 128 A rows and HALF of the W tile (BN/2 rows); the leader CTA issues tcgen05.mma.cta_group::2 with M = 256, each
+// SM's tensor core reads W halves from both SMs' shared memory, and every stage moves 32 KB instead of 48 KB per SM
+// at BN = 256 -- the single-CTA kernel is shared-memory-bandwidth bound (~65-70 % tensor-pipe active in ncu).
+// Barriers: TMA of both CTAs completes on the leader's full barrier; tcgen05.commit multicasts to both CTAs'
+// empty / tmem-full barriers; both CTAs' epilogue warps arrive on the leader's tmem-empty barrier.
+//
 // Epilogues (reference call sites, /root/reference/tld/transformer_blocks.py):
 //   EPI_BF16            out_bf16 = acc                                   qkv_linear            (:58)
 //   EPI_BIAS_BF16       out_bf16 = acc + bias                            mlp.0 1x1 conv D->4D  (:95)
@@ -51,10 +58,10 @@ constexpr int GEMM_THREADS = 256;
 constexpr int UMMA_K = 16;
 constexpr int STG_SLAB = 32 * 128;  // one epilogue warp's staging slab: 32 rows x 128 B
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CTAS = 1>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_BYTES = (BN / CTAS) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_BYTES = 4 * 2 * STG_SLAB;  // 4 warps x 2 buffers
   static constexpr int KV_BYTES = (EPI == EPI_XATTN_RESID_F32) ? 2 * 4 * BN * 4 : 0;  // 2 samples x {k0,k1,v0,v1}
@@ -73,11 +80,14 @@ __device__ __forceinline__ void stage_row(uint8_t* slab, int lane, const uint32_
   }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CTAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K, GemmEpi ep) {
-  using S = GemmSmem<BN, EPI>;
+  using S = GemmSmem<BN, EPI, CTAS>;
+  static_assert(CTAS == 1 || CTAS == 2, "CTAS must be 1 or 2");
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   constexpr int STAGES = S::STAGES;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                  : (2 * BN <= 256) ? 256 : 512;
@@ -100,10 +110,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+  constexpr int TILE_M = GEMM_BM * CTAS;  // rows per (cluster) tile
+  const int m_tiles = (M + TILE_M - 1) / TILE_M;
   const int n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = (K + GEMM_BK - 1) / GEMM_BK;
+  const int first_tile = blockIdx.x / CTAS;      // both CTAs of a pair walk the same tile sequence
+  const int tile_step = gridDim.x / CTAS;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmap_a);
@@ -112,21 +125,26 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], CTAS);   // one arrive per producer CTA (the leader's carries the expect_tx)
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], 4 * CTAS);  // one arrive per epilogue warp of every CTA in the pair
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CTAS == 2) {
+      tmem_alloc_pair(tmem_slot, TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -135,25 +153,32 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * GEMM_BM;
-        const int n0 = (tile % n_tiles) * BN;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * GEMM_BM;
+        const int n0 = (tile % n_tiles) * BN + int(cta_rank) * (BN / CTAS);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-          tma_load_2d(smem_a + stage * S::A_BYTES, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
-          tma_load_2d(smem_b + stage * S::B_BYTES, &tmap_b, &full_bar[stage], kb * GEMM_BK, n0);
+          if constexpr (CTAS == 2) {
+            if (leader) mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES * 2);
+            else mbar_arrive_cluster(mapa_u32(smem_u32(&full_bar[stage]), 0));
+            tma_load_2d_pair(smem_a + stage * S::A_BYTES, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
+            tma_load_2d_pair(smem_b + stage * S::B_BYTES, &tmap_b, &full_bar[stage], kb * GEMM_BK, n0);
+          } else {
+            mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+            tma_load_2d(smem_a + stage * S::A_BYTES, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
+            tma_load_2d(smem_b + stage * S::B_BYTES, &tmap_b, &full_bar[stage], kb * GEMM_BK, n0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, 0, 0);
+  } else if (warp == 1 && leader) {
+    // ===================== MMA issuer (leader CTA only when paired) =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -168,10 +193,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int k = 0; k < GEMM_BK / UMMA_K; ++k) {
             // advance 32 B (16 bf16) along K inside the 128 B swizzle row: +2 in the (addr>>4) field
-            umma_ss_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (CTAS == 2) umma_ss_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else umma_ss_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);                      // smem slot free once these MMAs retire
-          if (kb == k_blocks - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+          if constexpr (CTAS == 2) {
+            umma_commit_pair(&empty_bar[stage]);                      // frees this stage in BOTH CTAs
+            if (kb == k_blocks - 1) umma_commit_pair(&tfull_bar[acc]);  // accumulator halves complete in both CTAs
+          } else {
+            umma_commit(&empty_bar[stage]);                      // smem slot free once these MMAs retire
+            if (kb == k_blocks - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -202,10 +233,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     };
 
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile / n_tiles) * GEMM_BM;
+      const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * GEMM_BM;   // this CTA's 128 rows
       const int n0 = (tile % n_tiles) * BN;
       const int row = m0 + et;
       const int slab_row = m0 + ew * 32;
@@ -337,16 +368,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // accumulator stage drained: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (CTAS == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        else mbar_arrive(&tempty_bar[acc]);
+      }
     }
     if (lane == 0) bulk_wait<0>();  // all stores/reductions of this warp complete before the CTA may exit
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (CTAS == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

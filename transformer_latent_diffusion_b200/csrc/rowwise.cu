@@ -305,7 +305,7 @@ __device__ __forceinline__ void unpack4(const uint2& v, float (&f)[4]) {
   f[3] = __uint_as_float(v.y & 0xffff0000u);
 }
 
-__global__ void __launch_bounds__(256) dwconv_gelu_kernel(const bf16* __restrict__ h, const float* __restrict__ w9,
+__global__ void __launch_bounds__(256) dwconv_gelu_generic_kernel(const bf16* __restrict__ h, const float* __restrict__ w9,
                                                           const float* __restrict__ bias, bf16* __restrict__ g, int B,
                                                           int grid, int C) {
   const int c4n = C / 4;
@@ -370,13 +370,155 @@ __global__ void __launch_bounds__(256) dwconv_gelu_kernel(const bf16* __restrict
   }
 }
 
+// ---- packed-fp32 (FFMA2) helpers: sm_100a executes fma/mul/add on float2 operands in one instruction --------
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// exact-erf GELU on a channel pair (Abramowitz-Stegun 7.1.26, |erf err| <= 1.5e-7), packed arithmetic:
+//   z = |v|/sqrt2, t = 1/(1 + p z), erf(z) = 1 - (a1 t + .. + a5 t^5) exp(-z^2), gelu = v/2 (1 + sign(v) erf(z))
+__device__ __forceinline__ float2 gelu2(float2 v) {
+  const float2 av = make_float2(fabsf(v.x), fabsf(v.y));
+  const float2 den = ffma2(make_float2(0.3275911f * 0.70710678118654752f, 0.3275911f * 0.70710678118654752f), av,
+                           make_float2(1.f, 1.f));
+  const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+  float2 p = ffma2(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+  p = ffma2(p, t, make_float2(1.421413741f, 1.421413741f));
+  p = ffma2(p, t, make_float2(-0.284496736f, -0.284496736f));
+  p = ffma2(p, t, make_float2(0.254829592f, 0.254829592f));
+  // exp(-z^2) = 2^(-0.5 log2(e) v^2)
+  const float2 arg = fmul2(v, fmul2(v, make_float2(-0.72134752044448170f, -0.72134752044448170f)));
+  const float2 e = make_float2(ex2_approx(arg.x), ex2_approx(arg.y));
+  const float2 pte = fmul2(fmul2(p, t), e);
+  const float2 erf_abs = ffma2(pte, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+  const float2 hv = fmul2(v, make_float2(0.5f, 0.5f));
+  return ffma2(hv, make_float2(copysignf(erf_abs.x, v.x), copysignf(erf_abs.y, v.y)), hv);
+}
+
+// Specialised kernel for a compile-time token grid G (8/16/32/64): one thread = 4 channels (two FFMA2 pairs) of one
+// grid row, sliding along x.  y-borders: row index clamped + that tap row's weights zeroed (branch-free);
+// x-borders: zero columns.  Loads run 4 columns ahead of their use through a 6-deep raw-register ring.
+template <int G>
+__global__ void __launch_bounds__(256) dwconv_gelu_grid_kernel(const bf16* __restrict__ h, const float* __restrict__ w9,
+                                                               const float* __restrict__ bias, bf16* __restrict__ g,
+                                                               int B, int C) {
+  const int c4n = C >> 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * G * c4n) return;
+  const int c4 = idx % c4n;
+  const int rowid = idx / c4n;       // b * G + gy
+  const int gy = rowid % G;
+  const int c0 = c4 * 4;
+  const bool up = gy > 0, dn = gy + 1 < G;
+  float2 w[9][2];
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(w9 + (size_t)tp * C + c0));
+    const bool live = (tp / 3 == 1) || (tp / 3 == 0 ? up : dn);
+    w[tp][0] = live ? make_float2(a.x, a.y) : make_float2(0.f, 0.f);
+    w[tp][1] = live ? make_float2(a.z, a.w) : make_float2(0.f, 0.f);
+  }
+  const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + c0));
+  const float2 b0 = make_float2(bq.x, bq.y), b1 = make_float2(bq.z, bq.w);
+  const size_t rowC = (size_t)G * C;
+  const bf16* r1 = h + (size_t)rowid * rowC + c0;
+  const bf16* r0 = up ? r1 - rowC : r1;   // clamped rows: their weights are zero when out of range
+  const bf16* r2 = dn ? r1 + rowC : r1;
+  bf16* orow = g + (size_t)rowid * rowC + c0;
+
+  uint2 ring[6][3];       // raw columns, ring[c % 6]
+  float2 win[3][3][2];    // unpacked columns win[c % 3][dy][pair]
+  auto fetch = [&](uint2 (&dst)[3], int colx) {
+    if (colx < G) {
+      const size_t o = (size_t)colx * C;
+      dst[0] = *reinterpret_cast<const uint2*>(r0 + o);
+      dst[1] = *reinterpret_cast<const uint2*>(r1 + o);
+      dst[2] = *reinterpret_cast<const uint2*>(r2 + o);
+    } else {
+      dst[0] = dst[1] = dst[2] = make_uint2(0u, 0u);
+    }
+  };
+  auto unpack = [&](float2 (&dst)[3][2], const uint2 (&src)[3]) {
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      dst[dy][0] = unpack_bf16x2(src[dy].x);
+      dst[dy][1] = unpack_bf16x2(src[dy].y);
+    }
+  };
+#pragma unroll
+  for (int c = 0; c < 6; ++c) fetch(ring[c], c);
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) win[2][dy][0] = win[2][dy][1] = make_float2(0.f, 0.f);  // column -1
+  unpack(win[0], ring[0]);
+  unpack(win[1], ring[1]);
+
+  constexpr int U = (G % 12 == 0) ? 12 : (G <= 16 ? G : 12);
+#pragma unroll 1
+  for (int x0 = 0; x0 < G; x0 += U) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int xq = x0 + u;
+      if (G % U == 0 || xq < G) {
+        // x0 is a multiple of U (itself a multiple of 6 unless the loop runs once), so u stands in for xq in the
+        // compile-time ring/window indices
+        float2 a0 = b0, a1 = b1;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            a0 = ffma2(w[dy * 3 + dx][0], win[(u + dx + 2) % 3][dy][0], a0);
+            a1 = ffma2(w[dy * 3 + dx][1], win[(u + dx + 2) % 3][dy][1], a1);
+          }
+        const float2 g0 = gelu2(a0), g1 = gelu2(a1);
+        uint2 o;
+        o.x = pack_bf16x2_dev(g0.x, g0.y);
+        o.y = pack_bf16x2_dev(g1.x, g1.y);
+        *reinterpret_cast<uint2*>(orow + (size_t)xq * C) = o;
+        unpack(win[(u + 2) % 3], ring[(u + 2) % 6]);   // column xq+2 replaces column xq-1
+        fetch(ring[u % 6], xq + 6);                    // column xq+6 reuses the slot of column xq
+      }
+    }
+  }
+}
+
 int launch_dwconv_gelu(const bf16* h, const float* w9, const float* bias, bf16* g, int B, int grid, int C,
                        cudaStream_t st) {
   TLD_CHECK(C % 4 == 0, "dwconv: channel count must be a multiple of 4");
   TLD_CHECK(grid >= 2, "dwconv: token grid must be at least 2x2");
   const long long threads = (long long)B * grid * (C / 4);
+  TLD_CHECK(threads < (1LL << 31), "dwconv: problem too large for 32-bit thread indexing");
   const int blocks = int((threads + 255) / 256);
-  dwconv_gelu_kernel<<<blocks, 256, 0, st>>>(h, w9, bias, g, B, grid, C);
+  switch (grid) {
+    case 8: dwconv_gelu_grid_kernel<8><<<blocks, 256, 0, st>>>(h, w9, bias, g, B, C); break;
+    case 16: dwconv_gelu_grid_kernel<16><<<blocks, 256, 0, st>>>(h, w9, bias, g, B, C); break;
+    case 32: dwconv_gelu_grid_kernel<32><<<blocks, 256, 0, st>>>(h, w9, bias, g, B, C); break;
+    case 64: dwconv_gelu_grid_kernel<64><<<blocks, 256, 0, st>>>(h, w9, bias, g, B, C); break;
+    default: dwconv_gelu_generic_kernel<<<blocks, 256, 0, st>>>(h, w9, bias, g, B, grid, C);
+  }
   TLD_CUDA_OK(cudaGetLastError());
   return 0;
 }
