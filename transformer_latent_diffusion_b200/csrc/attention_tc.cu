@@ -205,7 +205,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       tma_reduce_add_2d(&tmap_x, slab, col_q, row_q + warp * 32);
       tma_reduce_add_2d(&tmap_x, slab + 32 * 128, col_q + 32, row_q + warp * 32);
       bulk_commit();
-      bulk_wait<0>();
+      bulk_wait_read<0>();
     }
   }
   tc_fence_before();

@@ -125,7 +125,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], CTAS);   // one arrive per producer CTA (the leader's carries the expect_tx)
+      mbar_init(&full_bar[s], 1);      // the leader's expect_tx arrive; the peer's TMA only adds complete_tx bytes
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -159,8 +159,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if constexpr (CTAS == 2) {
+            // Only the leader arms its barrier (for both CTAs' bytes).  The peer may run at most one phase ahead:
+            // its own empty barrier is released by the commit that follows the MMAs of the previous phase.
             if (leader) mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES * 2);
-            else mbar_arrive_cluster(mapa_u32(smem_u32(&full_bar[stage]), 0));
             tma_load_2d_pair(smem_a + stage * S::A_BYTES, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
             tma_load_2d_pair(smem_b + stage * S::B_BYTES, &tmap_b, &full_bar[stage], kb * GEMM_BK, n0);
           } else {
@@ -373,7 +374,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         else mbar_arrive(&tempty_bar[acc]);
       }
     }
-    if (lane == 0) bulk_wait<0>();  // all stores/reductions of this warp complete before the CTA may exit
+    if (lane == 0) bulk_wait_read<0>();  // staging slabs fully read by the TMA unit before the CTA may exit
   }
 
   tc_fence_before();

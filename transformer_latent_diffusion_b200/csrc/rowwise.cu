@@ -4,6 +4,7 @@
 #include <math.h>
 
 #include "common.h"
+#include "ptx.cuh"
 
 namespace tld {
 
@@ -394,11 +395,6 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 // exact-erf GELU on a channel pair (Abramowitz-Stegun 7.1.26, |erf err| <= 1.5e-7), packed arithmetic:
 //   z = |v|/sqrt2, t = 1/(1 + p z), erf(z) = 1 - (a1 t + .. + a5 t^5) exp(-z^2), gelu = v/2 (1 + sign(v) erf(z))
 __device__ __forceinline__ float2 gelu2(float2 v) {
@@ -505,6 +501,80 @@ __global__ void __launch_bounds__(256) dwconv_gelu_grid_kernel(const bf16* __res
   }
 }
 
+// 16x16 token grid (256-px latents), shared-memory version: one CTA = one image x 64 channels.  The whole
+// [256 positions x 64 ch] bf16 slab (32 KB) arrives with ONE TMA load (128B swizzle); lane = channel pair, so every
+// warp-wide LDS reads one full 128-byte row (conflict-free); warp w produces grid rows 2w and 2w+1 sliding along x
+// with a 4-row x 3-column fp32 window.  All shared-memory offsets are compile-time constants after unrolling.
+__global__ void __launch_bounds__(256) dwconv_gelu_g16_kernel(const __grid_constant__ CUtensorMap tmap_h,
+                                                              const float* __restrict__ w9,
+                                                              const float* __restrict__ bias, bf16* __restrict__ g,
+                                                              int C) {
+  constexpr int G = 16;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tile = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tile + G * G * 128);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.x * 64, b = blockIdx.y;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    mbar_expect_tx(bar, G * G * 128);
+    tma_load_2d(tile, &tmap_h, bar, c0, b * G * G);
+  }
+  // weights / bias of this lane's channel pair while the tile is in flight
+  const int ch = c0 + 2 * lane;
+  float2 w[9];
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp) w[tp] = __ldg(reinterpret_cast<const float2*>(w9 + (size_t)tp * C + ch));
+  const float2 bs = __ldg(reinterpret_cast<const float2*>(bias + ch));
+  __syncthreads();  // barrier init visible before anyone polls it
+  mbar_wait(bar, 0);
+
+  const int y0 = 2 * warp;  // output rows y0, y0+1; input rows y0-1 .. y0+2
+  const bool up = y0 > 0, dn = y0 + 2 < G;
+  // byte offset of (row rr of the 4-row window, column x) for this lane: p = y*16 + x, p & 7 == x & 7
+  const uint32_t rows = smem_u32(tile) + (y0 - 1) * G * 128;  // shared-window address (may point one row above)
+  const int lane_chunk = lane >> 2, lane_off = (lane & 3) * 4;
+  auto ldcol = [&](float2 (&dst)[4], int x) {
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const bool ok = (rr == 1 || rr == 2) || (rr == 0 ? up : dn);
+      uint32_t v = 0u;
+      if (ok) {
+        const uint32_t addr = rows + (rr * G + x) * 128 + ((lane_chunk ^ (x & 7)) << 4) + lane_off;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+      }
+      dst[rr] = unpack_bf16x2(v);
+    }
+  };
+  float2 win[3][4];
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) win[2][rr] = make_float2(0.f, 0.f);  // column -1
+  ldcol(win[0], 0);
+  ldcol(win[1], 1);
+  bf16* out = g + ((size_t)b * G * G + (size_t)y0 * G) * C + ch;
+#pragma unroll
+  for (int x = 0; x < G; ++x) {
+    float2 a0 = bs, a1 = bs;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        a0 = ffma2(w[dy * 3 + dx], win[(x + dx + 2) % 3][dy], a0);
+        a1 = ffma2(w[dy * 3 + dx], win[(x + dx + 2) % 3][dy + 1], a1);
+      }
+    const float2 g0 = gelu2(a0), g1 = gelu2(a1);
+    *reinterpret_cast<uint32_t*>(out + (size_t)x * C) = pack_bf16x2_dev(g0.x, g0.y);
+    *reinterpret_cast<uint32_t*>(out + (size_t)(G + x) * C) = pack_bf16x2_dev(g1.x, g1.y);
+    if (x + 2 < G) {
+      ldcol(win[(x + 2) % 3], x + 2);
+    } else {
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) win[(x + 2) % 3][rr] = make_float2(0.f, 0.f);
+    }
+  }
+}
+
 int launch_dwconv_gelu(const bf16* h, const float* w9, const float* bias, bf16* g, int B, int grid, int C,
                        cudaStream_t st) {
   TLD_CHECK(C % 4 == 0, "dwconv: channel count must be a multiple of 4");
@@ -512,6 +582,14 @@ int launch_dwconv_gelu(const bf16* h, const float* w9, const float* bias, bf16* 
   const long long threads = (long long)B * grid * (C / 4);
   TLD_CHECK(threads < (1LL << 31), "dwconv: problem too large for 32-bit thread indexing");
   const int blocks = int((threads + 255) / 256);
+  if (grid == 16 && C % 64 == 0 && B <= 65535) {
+    constexpr int smem = 1024 + 16 * 16 * 128 + 64;
+    CUtensorMap th;
+    if (make_tmap_2d(&th, h, false, (long long)B * 256, C, C, 256)) return 1;
+    dwconv_gelu_g16_kernel<<<dim3(C / 64, B), 256, smem, st>>>(th, w9, bias, g, C);
+    TLD_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   switch (grid) {
     case 8: dwconv_gelu_grid_kernel<8><<<blocks, 256, 0, st>>>(h, w9, bias, g, B, C); break;
     case 16: dwconv_gelu_grid_kernel<16><<<blocks, 256, 0, st>>>(h, w9, bias, g, B, C); break;
