@@ -101,6 +101,19 @@ TLD_API int tld_op_self_attention(const uint16_t* qkv, float* x, int batch, int 
 TLD_API int tld_op_dwconv_gelu(const uint16_t* h, const float* w9, const float* bias, uint16_t* g, int batch, int grid,
                        int channels, void* stream);
 
+/* ---- VAE decoder row-wise kernels (diffusers AutoencoderKL.decode, called at tld/diffusion.py:91) ------------
+ * NHWC bf16 activations (== torch channels_last).  y = act(GroupNorm_groups(x + pre_bias) * gamma + beta), act = SiLU
+ * if silu != 0; x,y [batch, hw, channels]; pre_bias (nullable: the producing conv's bias, folded in), gamma, beta
+ * fp32 [channels]. */
+TLD_API int tld_vae_group_norm(const uint16_t* x, const float* pre_bias, const float* gamma, const float* beta,
+                               uint16_t* y, int batch, int hw, int channels, int groups, float eps, int silu,
+                               void* stream);
+/* out = x + h + bias[c] (ResnetBlock2D tail; bias nullable), NHWC bf16, numel elements */
+TLD_API int tld_vae_add_bias(const uint16_t* x, const uint16_t* h, const float* bias, uint16_t* out, long long numel,
+                             int channels, void* stream);
+/* nearest-neighbour 2x upsample, NHWC bf16: x [batch,h,w,channels] -> y [batch,2h,2w,channels] */
+TLD_API int tld_vae_upsample2x(const uint16_t* x, uint16_t* y, int batch, int h, int w, int channels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

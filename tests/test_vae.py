@@ -47,6 +47,57 @@ def test_decode_matches_oracle_cpu():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("B,C,H", [(2, 128, 16), (3, 256, 8), (1, 512, 32), (2, 128, 64)])
+def test_group_norm_silu_kernel(B, C, H):
+    """tld_vae_group_norm (fused GroupNorm+SiLU, NHWC bf16) against torch fp32 on the same bf16 inputs."""
+    from transformer_latent_diffusion_b200 import _lib
+
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    x = (torch.randn(B, C, H, H, device="cuda", generator=g) * 2 + 0.5).bfloat16().contiguous(memory_format=torch.channels_last)
+    w = torch.randn(C, device="cuda", generator=g)
+    b = torch.randn(C, device="cuda", generator=g)
+    for silu in (0, 1):
+        ref = torch.nn.functional.group_norm(x.float(), 32, w, b, 1e-6)
+        ref = torch.nn.functional.silu(ref) if silu else ref
+        y = torch.empty_like(x)
+        _lib.check(_lib.load().tld_vae_group_norm(x.data_ptr(), None, w.data_ptr(), b.data_ptr(), y.data_ptr(), B, H * H, C, 32,
+                                                  1e-6, silu, torch.cuda.current_stream().cuda_stream), "gn")
+        assert y.is_contiguous(memory_format=torch.channels_last)
+        assert rel_fro(y.float(), ref) < 4e-3
+        pb = torch.randn(C, device="cuda", generator=g)
+        ref2 = torch.nn.functional.group_norm(x.float() + pb.view(1, -1, 1, 1), 32, w, b, 1e-6)
+        ref2 = torch.nn.functional.silu(ref2) if silu else ref2
+        _lib.check(_lib.load().tld_vae_group_norm(x.data_ptr(), pb.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), B, H * H, C,
+                                                  32, 1e-6, silu, torch.cuda.current_stream().cuda_stream), "gn")
+        assert rel_fro(y.float(), ref2) < 4e-3
+    h2 = torch.randn_like(x)
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().tld_vae_add_bias(x.data_ptr(), h2.data_ptr(), b.data_ptr(), out.data_ptr(), x.numel(), C,
+                                            torch.cuda.current_stream().cuda_stream), "add")
+    assert rel_fro(out.float(), x.float() + h2.float() + b.view(1, -1, 1, 1)) < 4e-3
+    up = torch.empty(B, C, 2 * H, 2 * H, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    _lib.check(_lib.load().tld_vae_upsample2x(x.data_ptr(), up.data_ptr(), B, H, H, C, torch.cuda.current_stream().cuda_stream), "up")
+    assert torch.equal(up, torch.nn.functional.interpolate(x, scale_factor=2.0, mode="nearest"))
+
+
+@pytest.mark.gpu
+def test_decode_gpu_fused_kernels_match_oracle():
+    """block widths that take the fused GroupNorm/upsample kernels (channels/32 multiple of 4)"""
+    from oracle import vae_oracle as V
+    from transformer_latent_diffusion_b200.vae import AutoencoderKLDecoder
+
+    torch.manual_seed(1)
+    m = AutoencoderKLDecoder(block_out=(128, 128, 256, 256))
+    for k, p in m.named_parameters():
+        if p.ndim == 1:
+            p.data.add_(0.1 * torch.randn_like(p))
+    z = torch.randn(2, 4, 8, 8)
+    ref = V.decode({k: v.detach() for k, v in m.state_dict().items()}, z)
+    (img,) = m.cuda().to(torch.bfloat16).decode(z.cuda())
+    assert rel_fro(img, ref) < 8e-2
+
+
+@pytest.mark.gpu
 def test_decode_gpu_bf16_matches_oracle():
     from oracle import vae_oracle as V
 

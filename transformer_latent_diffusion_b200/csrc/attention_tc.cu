@@ -58,6 +58,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       mbar_init(bar_p, 128);
       mbar_init(bar_o, 1);
       fence_mbar_init();
+      // first loads go out before the TMEM allocation / CTA-wide sync
+      mbar_expect_tx(bar_q, TA_Q_BYTES);
+      tma_load_2d(sQ, &tmap_qkv, bar_q, col_q, row_q);
+      mbar_expect_tx(bar_k, TA_K_BYTES);
+      tma_load_2d(sK, &tmap_qkv, bar_k, col_k, row_k);
+      mbar_expect_tx(bar_v, TA_K_BYTES);
+      tma_load_2d(sV, &tmap_qkv, bar_v, col_v, row_k);
     }
     __syncwarp();
     tmem_alloc(tmem_slot, 256);
@@ -75,45 +82,44 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(TA_BQ, TA_BK, 0, 0);   // S = Q K^T : both K-major
       constexpr uint32_t idesc_o = umma_idesc_bf16(TA_BQ, TA_HD, 0, 1);   // O = P V   : B (V) is MN-major
-      mbar_expect_tx(bar_q, TA_Q_BYTES);
-      tma_load_2d(sQ, &tmap_qkv, bar_q, col_q, row_q);
-      mbar_expect_tx(bar_k, TA_K_BYTES);
-      tma_load_2d(sK, &tmap_qkv, bar_k, col_k, row_k);
-      mbar_expect_tx(bar_v, TA_K_BYTES);
-      tma_load_2d(sV, &tmap_qkv, bar_v, col_v, row_k);
+      const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+      const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sK), 16, 1024);
+      auto issue_s = [&]() {
+#pragma unroll
+        for (int k = 0; k < TA_HD / 16; ++k) umma_ss_f16(tmem_s, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+        umma_commit(bar_s);
+      };
       mbar_wait(bar_q, 0);
+      mbar_wait(bar_k, 0);
+      tc_fence_after();
+      issue_s();
       for (int c = 0; c < n_chunks; ++c) {
         const uint32_t ph = c & 1;
-        mbar_wait(bar_k, ph);
-        tc_fence_after();
-        {
-          const uint64_t adesc = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
-          const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sK), 16, 1024);
-#pragma unroll
-          for (int k = 0; k < TA_HD / 16; ++k) umma_ss_f16(tmem_s, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
-          umma_commit(bar_s);
-        }
-        mbar_wait(bar_s, ph);  // S complete -> the K buffer is free for the next chunk
-        if (c + 1 < n_chunks) {
+        const bool more = c + 1 < n_chunks;
+        mbar_wait(bar_s, ph);  // S(c) complete -> the K buffer is free
+        if (more) {
           mbar_expect_tx(bar_k, TA_K_BYTES);
           tma_load_2d(sK, &tmap_qkv, bar_k, col_k, row_k + (c + 1) * TA_BK);
         }
-        mbar_wait(bar_p, ph);  // P written (and S fully read) by all 128 softmax threads
+        mbar_wait(bar_p, ph);  // P(c) written and S(c) fully read by all 128 softmax threads
         mbar_wait(bar_v, ph);
         tc_fence_after();
-        {
 #pragma unroll
-          for (int kk = 0; kk < TA_BK / 16; ++kk) {
-            // A: P sub-tile kk/4 ([128 x 64] K-major), 32 B per k-step inside the swizzle row
-            const uint64_t adesc = umma_smem_desc_sw128(smem_u32(sP + (kk >> 2) * (TA_BQ * 128)), 16, 1024) + 2 * (kk & 3);
-            // B: V rows kk*16.. (keys) x 64 hd, MN-major: 8-key groups are 1024 B apart (SBO)
-            const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sV + kk * 16 * 128), TA_BK * 128, 1024);
-            umma_ss_f16(tmem_o, adesc, bdesc, idesc_o, kk != 0);
-          }
-          umma_commit(bar_o);
+        for (int kk = 0; kk < TA_BK / 16; ++kk) {
+          // A: P sub-tile kk/4 ([128 x 64] K-major), 32 B per k-step inside the swizzle row
+          const uint64_t adesc = umma_smem_desc_sw128(smem_u32(sP + (kk >> 2) * (TA_BQ * 128)), 16, 1024) + 2 * (kk & 3);
+          // B: V rows kk*16.. (keys) x 64 hd, MN-major: 8-key groups are 1024 B apart (SBO)
+          const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sV + kk * 16 * 128), TA_BK * 128, 1024);
+          umma_ss_f16(tmem_o, adesc, bdesc, idesc_o, kk != 0);
         }
-        mbar_wait(bar_o, ph);  // O chunk complete -> V and P buffers are free
-        if (c + 1 < n_chunks) {
+        umma_commit(bar_o);
+        if (more) {  // S(c+1) runs behind PV(c) on the tensor pipe while the softmax threads read O(c)
+          mbar_wait(bar_k, ph ^ 1);
+          tc_fence_after();
+          issue_s();
+        }
+        mbar_wait(bar_o, ph);  // O(c) complete -> V and P buffers are free
+        if (more) {
           mbar_expect_tx(bar_v, TA_K_BYTES);
           tma_load_2d(sV, &tmap_qkv, bar_v, col_v, row_k + (c + 1) * TA_BK);
         }
@@ -153,13 +159,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         tmem_ld_x32(tmem_s + lane_base + j * 32, s);
         tmem_ld_wait();
         uint32_t pk[16];
+        float2 rs2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * i]), sl2, -mb));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), sl2, -mb));
-          rs += p0 + p1;
-          pk[i] = pack_bf16x2(p0, p1);
+          const float2 a = ffma2(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])),
+                                 make_float2(sl2, sl2), make_float2(-mb, -mb));
+          const float2 p = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+          rs2 = fadd2(rs2, p);
+          pk[i] = pack_bf16x2(p.x, p.y);
         }
+        rs += rs2.x + rs2.y;
         uint8_t* sub = sP + (j >> 1) * (TA_BQ * 128) + r * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {

@@ -371,22 +371,7 @@ __global__ void __launch_bounds__(256) dwconv_gelu_generic_kernel(const bf16* __
   }
 }
 
-// ---- packed-fp32 (FFMA2) helpers: sm_100a executes fma/mul/add on float2 operands in one instruction --------
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;"
-      : "=l"(d)
-      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
-        "l"(*reinterpret_cast<unsigned long long*>(&c)));
-  return *reinterpret_cast<float2*>(&d);
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-  unsigned long long d;
-  asm("mul.rn.f32x2 %0, %1, %2;"
-      : "=l"(d)
-      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
-  return *reinterpret_cast<float2*>(&d);
-}
+// packed-fp32 (FFMA2) helpers ffma2()/fmul2() live in ptx.cuh
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t w) {
   return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
 }

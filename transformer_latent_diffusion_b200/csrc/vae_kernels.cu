@@ -1,0 +1,218 @@
+// Row-wise kernels of the VAE decoder, NHWC bf16 activations:
+//   GroupNorm(32 groups, eps) [+ SiLU] fused into two HBM passes (statistics, then normalise+affine+SiLU), and the
+//   nearest-neighbour 2x upsample.  In the PyTorch library path these are 72 % of the decode time (ATen's
+//   channels-last GroupNorm + separate SiLU/elementwise kernels); the 3x3 convolutions stay on cuDNN in round 1.
+// Reference call site: tld/diffusion.py:91 -> diffusers AutoencoderKL.decode (ResnetBlock2D: GroupNorm -> SiLU ->
+// conv3x3, UpSample2D: nearest 2x -> conv3x3).
+#include "common.h"
+
+namespace tld {
+
+__device__ __forceinline__ void bf16x8_to_float(const uint4& v, float (&f)[8]) {
+  f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+  f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+  f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+  f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t pk2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// partial[b][blk][g] = (sum, sum of squares) of group g over the block's pixel range
+__global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, const float* __restrict__ pre_bias,
+                                                       float2* __restrict__ partial, int HW, int C, int groups,
+                                                       int pix_per_block) {
+  __shared__ float s_sum[64], s_sq[64];
+  const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+  const int tpp = C >> 3;                 // threads per pixel (8 channels = 16 bytes each)
+  const int cpg = C / groups;             // channels per group
+  const int cv = threadIdx.x % tpp, poff = threadIdx.x / tpp, pstride = 256 / tpp;
+  if (threadIdx.x < 64) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+  __syncthreads();
+  const int p0 = blk * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+  const bf16* xb = x + (size_t)b * HW * C + cv * 8;
+  float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;  // first / second half of the 8 channels
+  float pb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) pb[j] = pre_bias ? pre_bias[cv * 8 + j] : 0.f;
+  for (int p = p0 + poff; p < p1; p += pstride) {
+    const uint4 v = *reinterpret_cast<const uint4*>(xb + (size_t)p * C);
+    float f[8];
+    bf16x8_to_float(v, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += pb[j];
+    s0 += (f[0] + f[1]) + (f[2] + f[3]);
+    q0 += (f[0] * f[0] + f[1] * f[1]) + (f[2] * f[2] + f[3] * f[3]);
+    s1 += (f[4] + f[5]) + (f[6] + f[7]);
+    q1 += (f[4] * f[4] + f[5] * f[5]) + (f[6] * f[6] + f[7] * f[7]);
+  }
+  const int g0 = (cv * 8) / cpg, g1 = (cv * 8 + 4) / cpg;
+  if (g0 == g1) {
+    atomicAdd(&s_sum[g0], s0 + s1);
+    atomicAdd(&s_sq[g0], q0 + q1);
+  } else {
+    atomicAdd(&s_sum[g0], s0); atomicAdd(&s_sq[g0], q0);
+    atomicAdd(&s_sum[g1], s1); atomicAdd(&s_sq[g1], q1);
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) partial[((size_t)b * nblk + blk) * groups + threadIdx.x] = make_float2(s_sum[threadIdx.x], s_sq[threadIdx.x]);
+}
+
+// y = act((x - mean_g) * rstd_g * gamma_c + beta_c), act = SiLU or identity
+__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ pre_bias,
+                                                       const float2* __restrict__ partial, int n_partial,
+                                                       const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, bf16* __restrict__ y, int HW, int C,
+                                                       int groups, float eps, int silu, int pix_per_block) {
+  __shared__ float s_a[512], s_b[512], s_mean[64], s_rstd[64];
+  const int b = blockIdx.y, blk = blockIdx.x;
+  const int cpg = C / groups;
+  if (threadIdx.x < groups) {
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < n_partial; ++i) {
+      const float2 v = partial[((size_t)b * n_partial + i) * groups + threadIdx.x];
+      s += v.x; q += v.y;
+    }
+    const double n = (double)HW * cpg;
+    const double mean = s / n;
+    const double var = fmax(q / n - mean * mean, 0.0);
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const int g = c / cpg;
+    const float a = s_rstd[g] * gamma[c];
+    s_a[c] = a;
+    s_b[c] = beta[c] + ((pre_bias ? pre_bias[c] : 0.f) - s_mean[g]) * a;  // (x + pb - mean) * a + beta
+  }
+  __syncthreads();
+  const int tpp = C >> 3;
+  const int cv = threadIdx.x % tpp, poff = threadIdx.x / tpp, pstride = 256 / tpp;
+  float a[8], bb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a[j] = s_a[cv * 8 + j]; bb[j] = s_b[cv * 8 + j]; }
+  const int p0 = blk * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+  const size_t base = (size_t)b * HW * C + cv * 8;
+  for (int p = p0 + poff; p < p1; p += pstride) {
+    const uint4 v = *reinterpret_cast<const uint4*>(x + base + (size_t)p * C);
+    float f[8];
+    bf16x8_to_float(v, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = fmaf(f[j], a[j], bb[j]);
+      if (silu) t = t / (1.0f + __expf(-t));
+      f[j] = t;
+    }
+    uint4 o;
+    o.x = pk2(f[0], f[1]); o.y = pk2(f[2], f[3]); o.z = pk2(f[4], f[5]); o.w = pk2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(y + base + (size_t)p * C) = o;
+  }
+}
+
+// nearest-neighbour 2x upsample, NHWC: each thread copies one 16-byte channel vector to its 4 output pixels
+__global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H,
+                                                         int W, int C8) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * H * W * C8;
+  if (idx >= total) return;
+  const int c = int(idx % C8);
+  const long long pix = idx / C8;
+  const int xw = int(pix % W);
+  const int yh = int((pix / W) % H);
+  const long long b = pix / ((long long)W * H);
+  const uint4 v = x[idx];
+  const long long orow = ((b * 2 * H + 2 * yh) * 2 * W + 2 * xw) * C8 + c;
+  y[orow] = v;
+  y[orow + C8] = v;
+  y[orow + 2LL * W * C8] = v;
+  y[orow + 2LL * W * C8 + C8] = v;
+}
+
+static float2* g_partial = nullptr;
+static size_t g_partial_cap = 0;
+
+// out = x + h + bias[c]  (ResnetBlock2D tail: shortcut + conv2 output, with conv2's bias folded in)
+__global__ void __launch_bounds__(256) add_bias_kernel(const uint4* __restrict__ x, const uint4* __restrict__ h,
+                                                       const float* __restrict__ bias, uint4* __restrict__ out,
+                                                       long long n_vec, int C8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_vec) return;
+  const int c = int(i % C8) * 8;
+  float a[8], b[8];
+  bf16x8_to_float(x[i], a);
+  bf16x8_to_float(h[i], b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] += b[j] + (bias ? bias[c + j] : 0.f);
+  uint4 o;
+  o.x = pk2(a[0], a[1]); o.y = pk2(a[2], a[3]); o.z = pk2(a[4], a[5]); o.w = pk2(a[6], a[7]);
+  out[i] = o;
+}
+
+int launch_add_bias(const bf16* x, const bf16* h, const float* bias, bf16* out, long long n, int C, cudaStream_t st) {
+  TLD_CHECK(C % 8 == 0 && n % 8 == 0, "add_bias: channels must be a multiple of 8");
+  const long long nv = n / 8;
+  add_bias_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(x),
+                                                                reinterpret_cast<const uint4*>(h), bias,
+                                                                reinterpret_cast<uint4*>(out), nv, C / 8);
+  TLD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_gn_act(const bf16* x, const float* pre_bias, const float* gamma, const float* beta, bf16* y, int B, int HW,
+                  int C, int groups, float eps, int silu, cudaStream_t st) {
+  TLD_CHECK(C % 8 == 0 && C <= 512 && (256 % (C / 8)) == 0, "group_norm: channels must be 128/256/512-like (C/8 divides 256)");
+  TLD_CHECK(groups <= 64 && C % groups == 0 && (C / groups) % 4 == 0, "group_norm: bad group configuration");
+  TLD_CHECK(B <= 65535, "group_norm: batch too large");
+  // enough blocks to fill the machine, at least 256 pixels per block
+  int nblk = (HW + 2047) / 2048;
+  const int want = (4 * sm_count() + B - 1) / B;
+  if (nblk < want) nblk = want;
+  int ppb = (HW + nblk - 1) / nblk;
+  const int pstride = 256 / (C / 8);
+  ppb = ((ppb + pstride - 1) / pstride) * pstride;
+  nblk = (HW + ppb - 1) / ppb;
+  const size_t need = (size_t)B * nblk * groups;
+  if (need > g_partial_cap) {
+    if (g_partial) cudaFree(g_partial);
+    TLD_CUDA_OK(cudaMalloc(&g_partial, need * sizeof(float2)));
+    g_partial_cap = need;
+  }
+  gn_stats_kernel<<<dim3(nblk, B), 256, 0, st>>>(x, pre_bias, g_partial, HW, C, groups, ppb);
+  TLD_CUDA_OK(cudaGetLastError());
+  gn_apply_kernel<<<dim3(nblk, B), 256, 0, st>>>(x, pre_bias, g_partial, nblk, gamma, beta, y, HW, C, groups, eps, silu, ppb);
+  TLD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_upsample2x(const bf16* x, bf16* y, int B, int H, int W, int C, cudaStream_t st) {
+  TLD_CHECK(C % 8 == 0, "upsample: channels must be a multiple of 8");
+  const long long total = (long long)B * H * W * (C / 8);
+  upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(x),
+                                                                    reinterpret_cast<uint4*>(y), B, H, W, C / 8);
+  TLD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace tld
+
+extern "C" {
+__attribute__((visibility("default"))) int tld_vae_group_norm(const uint16_t* x, const float* pre_bias,
+                                                              const float* gamma, const float* beta, uint16_t* y,
+                                                              int batch, int hw, int channels, int groups, float eps,
+                                                              int silu, void* stream) {
+  return tld::launch_gn_act(reinterpret_cast<const tld::bf16*>(x), pre_bias, gamma, beta, reinterpret_cast<tld::bf16*>(y),
+                            batch, hw, channels, groups, eps, silu, reinterpret_cast<cudaStream_t>(stream));
+}
+__attribute__((visibility("default"))) int tld_vae_add_bias(const uint16_t* x, const uint16_t* h, const float* bias,
+                                                            uint16_t* out, long long numel, int channels, void* stream) {
+  return tld::launch_add_bias(reinterpret_cast<const tld::bf16*>(x), reinterpret_cast<const tld::bf16*>(h), bias,
+                              reinterpret_cast<tld::bf16*>(out), numel, channels, reinterpret_cast<cudaStream_t>(stream));
+}
+__attribute__((visibility("default"))) int tld_vae_upsample2x(const uint16_t* x, uint16_t* y, int batch, int h, int w,
+                                                              int channels, void* stream) {
+  return tld::launch_upsample2x(reinterpret_cast<const tld::bf16*>(x), reinterpret_cast<tld::bf16*>(y), batch, h, w,
+                                channels, reinterpret_cast<cudaStream_t>(stream));
+}
+}

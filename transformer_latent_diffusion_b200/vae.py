@@ -8,9 +8,11 @@ diffusers/SDXL-VAE structure with diffusers-compatible ``state_dict`` keys (``po
 ``decoder.conv_out``) so the real checkpoint loads when it is available, and is checked against the independent
 fp32 restatement in ``oracle/vae_oracle.py`` with random weights.
 
-ROUND-1 STATUS: the convolutions/GroupNorm here run on PyTorch's library kernels (cuDNN implicit-GEMM, ATen
-GroupNorm) in bf16/channels-last -- this is the one place on the north-star path that is not yet hand-written
-sm_100a code (see DESIGN.md "VAE decode").  bench.py reports the denoiser-only number next to the end-to-end one.
+ROUND-1 STATUS: on CUDA/bf16 the GroupNorm(+SiLU) and nearest-2x upsample stages run on hand-written kernels
+(``csrc/vae_kernels.cu`` through ``tld_vae_group_norm`` / ``tld_vae_upsample2x``; in the stock ATen path they were 72 %
+of the decode time); the 3x3/1x1 convolutions and the single mid-block attention still run on PyTorch's library
+kernels (cuDNN implicit GEMM) -- the one part of the north-star path that is not yet hand-written sm_100a code (see
+DESIGN.md "VAE decode").  bench.py reports the denoiser-only number next to the end-to-end one.
 """
 from __future__ import annotations
 
@@ -111,22 +113,81 @@ class AutoencoderKLDecoder(nn.Module):
         return mod._parameters[leaf]
 
     # -- building blocks ---------------------------------------------------------------------------------------
-    def _conv(self, x, name, pad):
-        return F.conv2d(x, self._p(name + ".weight"), self._p(name + ".bias"), padding=pad)
+    def _conv(self, x, name, pad, bias=True):
+        return F.conv2d(x, self._p(name + ".weight"), self._p(name + ".bias") if bias else None, padding=pad)
 
-    def _gn_silu(self, x, name):
-        return F.silu(F.group_norm(x, GN_GROUPS, self._p(name + ".weight"), self._p(name + ".bias"), GN_EPS))
+    def _f32(self, key: str, device) -> torch.Tensor:
+        """fp32 copy of a 1-D parameter for the fused kernels (cached per device)"""
+        cache = self.__dict__.setdefault("_f32_cache", {})
+        t = cache.get(key)
+        if t is None or t.device != device:
+            t = self._p(key).detach().to(device=device, dtype=torch.float32).contiguous()
+            cache[key] = t
+        return t
+
+    @staticmethod
+    def _fusable(x) -> bool:
+        Cc = x.shape[1]
+        return (x.is_cuda and x.dtype == torch.bfloat16 and Cc % 8 == 0 and Cc <= 512 and 256 % (Cc // 8) == 0
+                and (Cc // GN_GROUPS) % 4 == 0)
+
+    def _group_norm(self, x, name, silu: bool, pre_bias=None):
+        """act(GroupNorm(32, eps 1e-6)(x + pre_bias)); fused sm_100a kernels for bf16 channels-last CUDA tensors.
+        ``pre_bias`` names the producing conv whose bias was left out of the conv call and is folded in here."""
+        Cc = x.shape[1]
+        if self._fusable(x):
+            from . import _lib
+
+            x = x.contiguous(memory_format=torch.channels_last)
+            y = torch.empty_like(x)  # keeps the NHWC strides
+            pb = self._f32(pre_bias + ".bias", x.device).data_ptr() if pre_bias else None
+            _lib.check(_lib.load().tld_vae_group_norm(
+                x.data_ptr(), pb, self._f32(name + ".weight", x.device).data_ptr(),
+                self._f32(name + ".bias", x.device).data_ptr(), y.data_ptr(), x.shape[0], x.shape[2] * x.shape[3], Cc,
+                GN_GROUPS, GN_EPS, int(silu), _lib.current_stream_ptr(x.device)), "tld_vae_group_norm")
+            return y
+        if pre_bias:
+            x = x + self._p(pre_bias + ".bias").view(1, -1, 1, 1)
+        h = F.group_norm(x, GN_GROUPS, self._p(name + ".weight"), self._p(name + ".bias"), GN_EPS)
+        return F.silu(h) if silu else h
+
+    def _add_bias(self, x, h, bias_of):
+        """x + h + bias (the skipped bias of conv `bias_of`)"""
+        if self._fusable(h) and x.shape == h.shape and x.dtype == h.dtype:
+            from . import _lib
+
+            x = x.contiguous(memory_format=torch.channels_last)
+            h = h.contiguous(memory_format=torch.channels_last)
+            out = torch.empty_like(h)
+            _lib.check(_lib.load().tld_vae_add_bias(x.data_ptr(), h.data_ptr(), self._f32(bias_of + ".bias", h.device).data_ptr(),
+                                                    out.data_ptr(), h.numel(), h.shape[1],
+                                                    _lib.current_stream_ptr(h.device)), "tld_vae_add_bias")
+            return out
+        return x + h + self._p(bias_of + ".bias").view(1, -1, 1, 1)
+
+    def _upsample2x(self, x):
+        if x.is_cuda and x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0:
+            from . import _lib
+
+            x = x.contiguous(memory_format=torch.channels_last)
+            B, Cc, H, W = x.shape
+            y = torch.empty((B, Cc, 2 * H, 2 * W), device=x.device, dtype=x.dtype).contiguous(memory_format=torch.channels_last)
+            _lib.check(_lib.load().tld_vae_upsample2x(x.data_ptr(), y.data_ptr(), B, H, W, Cc,
+                                                      _lib.current_stream_ptr(x.device)), "tld_vae_upsample2x")
+            return y
+        return F.interpolate(x, scale_factor=2.0, mode="nearest")
 
     def _resnet(self, x, name):
-        h = self._conv(self._gn_silu(x, name + ".norm1"), name + ".conv1", 1)
-        h = self._conv(self._gn_silu(h, name + ".norm2"), name + ".conv2", 1)
+        # conv biases are folded into the next fused kernel (GroupNorm input / residual add) instead of a separate pass
+        h = self._conv(self._group_norm(x, name + ".norm1", True), name + ".conv1", 1, bias=False)
+        h = self._conv(self._group_norm(h, name + ".norm2", True, pre_bias=name + ".conv1"), name + ".conv2", 1, bias=False)
         if (name + ".conv_shortcut.weight") in self._layout:
             x = self._conv(x, name + ".conv_shortcut", 0)
-        return x + h
+        return self._add_bias(x, h, name + ".conv2")
 
     def _mid_attention(self, x, name):
         B, Cc, H, W = x.shape
-        h = F.group_norm(x, GN_GROUPS, self._p(name + ".group_norm.weight"), self._p(name + ".group_norm.bias"), GN_EPS)
+        h = self._group_norm(x, name + ".group_norm", False)
         t = h.permute(0, 2, 3, 1).reshape(B, H * W, Cc)
         q = F.linear(t, self._p(name + ".to_q.weight"), self._p(name + ".to_q.bias"))
         k = F.linear(t, self._p(name + ".to_k.weight"), self._p(name + ".to_k.bias"))
@@ -146,9 +207,9 @@ class AutoencoderKLDecoder(nn.Module):
             for j in range(LAYERS_PER_BLOCK + 1):
                 x = self._resnet(x, f"decoder.up_blocks.{i}.resnets.{j}")
             if i != n_up - 1:
-                x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+                x = self._upsample2x(x)
                 x = self._conv(x, f"decoder.up_blocks.{i}.upsamplers.0.conv", 1)
-        x = self._gn_silu(x, "decoder.conv_norm_out")
+        x = self._group_norm(x, "decoder.conv_norm_out", True)
         return self._conv(x, "decoder.conv_out", 1)
 
     @torch.no_grad()
