@@ -111,6 +111,11 @@ TLD_API int tld_vae_group_norm(const uint16_t* x, const float* pre_bias, const f
 /* out = x + h + bias[c] (ResnetBlock2D tail; bias nullable), NHWC bf16, numel elements */
 TLD_API int tld_vae_add_bias(const uint16_t* x, const uint16_t* h, const float* bias, uint16_t* out, long long numel,
                              int channels, void* stream);
+/* 3x3 'same' convolution as an implicit GEMM on the tcgen05 core (4-D TMA boxes shifted per tap, zero fill = padding):
+ * x NHWC bf16 [batch,h,w,cin], w bf16 [cout, 9*cin] with K order (ky,kx,cin), bias fp32 [cout] or NULL,
+ * out NHWC bf16 [batch,h,w,cout]; cin,cout multiples of 64, h*w multiple of 128. */
+TLD_API int tld_vae_conv3x3(const uint16_t* x, const uint16_t* w, const float* bias, uint16_t* out, int batch, int h,
+                            int w_px, int cin, int cout, void* stream);
 /* nearest-neighbour 2x upsample, NHWC bf16: x [batch,h,w,channels] -> y [batch,2h,2w,channels] */
 TLD_API int tld_vae_upsample2x(const uint16_t* x, uint16_t* y, int batch, int h, int w, int channels, void* stream);
 

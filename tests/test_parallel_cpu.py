@@ -1,0 +1,61 @@
+"""World-size-2 gloo test of the batch-sharding host logic (no GPU): shards partition the batch, gather restores
+the original order, uneven batches work."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from transformer_latent_diffusion_b200.parallel import shard_bounds
+
+
+def test_shard_bounds_partition():
+    for n in (0, 1, 5, 8, 64, 67):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(4, 2, 2)
+
+
+class _FakeGenerator:
+    """stands in for DiffusionGenerator: 'sampling' is a deterministic function of (label, seed) so ordering shows"""
+
+    def generate_latents(self, labels, num_imgs, seeds, **kw):
+        assert labels.shape[0] == num_imgs == seeds.shape[0]
+        return seeds * 2 + labels[:, :1, None, None]
+
+
+def _worker(rank, world, port, n_imgs, out):
+    import torch.distributed as dist
+
+    from transformer_latent_diffusion_b200.parallel import generate_sharded
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    labels = torch.randn(n_imgs, 8, generator=g)
+    seeds = torch.randn(n_imgs, 4, 2, 2, generator=g)
+    res = generate_sharded(_FakeGenerator(), labels, seeds, dst=0)
+    if rank == 0:
+        torch.save((res, seeds * 2 + labels[:, :1, None, None]), out)
+    else:
+        assert res is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_imgs", [6, 5])
+def test_generate_sharded_gloo_world2(tmp_path, n_imgs):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(2, port, n_imgs, out), nprocs=2, join=True)
+    res, ref = torch.load(out)
+    assert torch.equal(res, ref)

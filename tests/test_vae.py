@@ -81,6 +81,35 @@ def test_group_norm_silu_kernel(B, C, H):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("ctas", [1, 2])
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 128, 128), (1, 32, 32, 512, 256), (3, 64, 64, 64, 192),
+                                            (1, 128, 128, 128, 64), (1, 8, 256, 64, 128)])
+def test_conv3x3_implicit_gemm(B, H, W, Cin, Cout, ctas):
+    """tld_vae_conv3x3 (tcgen05 implicit GEMM, 4-D TMA im2col) against torch conv2d in fp32 on the same bf16 data."""
+    from transformer_latent_diffusion_b200 import _lib
+
+    L = _lib.load()
+    _lib.check(L.tld_set_option(b"gemm_ctas", ctas), "opt")
+    try:
+        g = torch.Generator(device="cuda").manual_seed(H + Cin)
+        x = torch.randn(B, Cin, H, W, device="cuda", generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+        w = (torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (3 * Cin ** 0.5)).bfloat16()
+        bias = torch.randn(Cout, device="cuda", generator=g)
+        ref = torch.nn.functional.conv2d(x.float(), w.float(), bias, padding=1)
+        wp = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+        y = torch.full((B, Cout, H, W), float("nan"), device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        _lib.check(L.tld_vae_conv3x3(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), y.data_ptr(), B, H, W, Cin, Cout,
+                                     torch.cuda.current_stream().cuda_stream), "conv")
+        torch.cuda.synchronize()
+        assert torch.isfinite(y.float()).all()
+        assert rel_fro(y.float(), ref) < 4e-3
+        # borders exercise the TMA zero fill
+        assert rel_fro(y.float()[:, :, 0, :], ref[:, :, 0, :]) < 4e-3 and rel_fro(y.float()[:, :, :, -1], ref[:, :, :, -1]) < 4e-3
+    finally:
+        _lib.check(L.tld_set_option(b"gemm_ctas", 0), "opt")
+
+
+@pytest.mark.gpu
 def test_decode_gpu_fused_kernels_match_oracle():
     """block widths that take the fused GroupNorm/upsample kernels (channels/32 multiple of 4)"""
     from oracle import vae_oracle as V

@@ -93,6 +93,9 @@ int launch_cfg_update(const float* model_out, float* x_t, float* x0_prev, float*
                       const int* step_ptr, int B, int C, int hw, cudaStream_t st);
 int launch_advance_step(int* step_ptr, cudaStream_t st);
 
+// 3x3 'same' conv as implicit GEMM: x NHWC bf16, w bf16 [Cout, 9*Cin] with K order (ky,kx,cin), bias fp32 or null
+int launch_conv3x3(const bf16* x, const bf16* w, const float* bias, bf16* out, int B, int H, int W, int Cin, int Cout,
+                   cudaStream_t st);
 void set_gemm_ctas(int v);  // 0 auto, 1 single-CTA tiles, 2 CTA-pair tiles (experiments / tests)
 
 // 2-D row-major TMA descriptor (bf16 or fp32), box = [box_rows, 128 bytes], 128B swizzle (gemm.cu)

@@ -47,6 +47,20 @@ int make_tmap_2d(CUtensorMap* m, const void* base, bool is_f32, long long rows, 
 static int g_gemm_ctas = 0;  // 0 = auto, 1 = single-CTA tiles, 2 = CTA-pair (cta_group::2) tiles
 void set_gemm_ctas(int v) { g_gemm_ctas = v; }
 
+// 4-D NHWC bf16 activation tensor [B,H,W,C] for the implicit-GEMM conv: box = [64 ch, w_box, h_box, 1], 128B swizzle
+static int make_tmap_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int C, int w_box, int h_box) {
+  if (resolve_encode()) return fail("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64u, (cuuint32_t)w_box, (cuuint32_t)h_box, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(4d) failed, CUresult=" + std::to_string((int)r));
+  return 0;
+}
+
 template <int BN, int EPI, int CTAS>
 static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
                     const GemmEpi& ep, cudaStream_t st) {
@@ -112,6 +126,36 @@ static int pick_bn(int M, int N, int ctas) {
   return best;
 }
 
+static int dispatch(int ctas, int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M,
+                    int N, int K, const GemmEpi& ep, cudaStream_t st);
+
+// 3x3 'same' convolution as an implicit GEMM on the tcgen05 core: x NHWC bf16 [B,H,W,Cin], w bf16 [Cout, 9*Cin]
+// (K order = (ky, kx, cin)), bias fp32 [Cout] -> out NHWC bf16 [B,H,W,Cout].
+int launch_conv3x3(const bf16* x, const bf16* w, const float* bias, bf16* out, int B, int H, int W, int Cin, int Cout,
+                   cudaStream_t st) {
+  TLD_CHECK(Cin % 64 == 0 && Cout % 64 == 0, "conv3x3: Cin and Cout must be multiples of 64");
+  TLD_CHECK((H * W) % 128 == 0, "conv3x3: H*W must be a multiple of 128");
+  const int w_box = W < 128 ? W : 128;
+  TLD_CHECK(128 % w_box == 0 && W % w_box == 0, "conv3x3: width must divide 128 or be a multiple of 128");
+  const int h_box = 128 / w_box;
+  TLD_CHECK(H % h_box == 0, "conv3x3: height must be a multiple of 128/width");
+  const long long M = (long long)B * H * W;
+  TLD_CHECK(M < (1LL << 31), "conv3x3: too many pixels");
+  const int K = 9 * Cin, N = Cout;
+  const int ctas = g_gemm_ctas ? g_gemm_ctas : (M >= 4096 ? 2 : 1);
+  const int bn = pick_bn((int)M, N, ctas);
+  CUtensorMap ta, tb, tc;
+  if (make_tmap_nhwc(&ta, x, B, H, W, Cin, w_box, h_box)) return 1;
+  if (make_tmap_2d(&tb, w, false, N, K, K, bn / ctas)) return 1;
+  if (make_tmap_2d(&tc, out, false, M, N, N, 32)) return 1;
+  GemmEpi ep{};
+  ep.bias = bias;
+  ep.conv_cpb = Cin / 64;
+  ep.conv_h = H;
+  ep.conv_w = W;
+  return dispatch(ctas, bn, bias ? EPI_BIAS_BF16 : EPI_BF16, ta, tb, tc, (int)M, N, K, ep, st);
+}
+
 int launch_gemm(int epi, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, void* out, int ldo,
                 const float* bias, const XattnArgs* xa, cudaStream_t st) {
   TLD_CHECK(M > 0 && N > 0 && K > 0, "launch_gemm: empty problem");
@@ -147,6 +191,11 @@ int launch_gemm(int epi, const bf16* A, int lda, const bf16* W, int ldw, int M, 
     ep.n_tok = xa->n_tok;
     ep.embed_dim = xa->embed_dim;
   }
+  return dispatch(ctas, bn, epi, ta, tb, tc, M, N, K, ep, st);
+}
+
+static int dispatch(int ctas, int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M,
+                    int N, int K, const GemmEpi& ep, cudaStream_t st) {
   if (ctas == 2) {
     switch (bn) {
       case 256: return launch_bn<256, 2>(epi, ta, tb, tc, M, N, K, ep, st);
@@ -161,7 +210,7 @@ int launch_gemm(int epi, const bf16* A, int lda, const bf16* W, int ldw, int M, 
     case 128: return launch_bn<128, 1>(epi, ta, tb, tc, M, N, K, ep, st);
     case 64: return launch_bn<64, 1>(epi, ta, tb, tc, M, N, K, ep, st);
   }
-  return fail("launch_gemm: no tile width for N=" + std::to_string(N));
+  return fail("gemm dispatch: no tile width for N=" + std::to_string(N));
 }
 
 }  // namespace tld

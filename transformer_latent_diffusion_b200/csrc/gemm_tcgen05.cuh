@@ -50,6 +50,10 @@ struct GemmEpi {
   int n_tok;          // tokens per sample (row -> sample = row / n_tok)
   int embed_dim;      // D
   float scale;        // 1/sqrt(head_dim)
+  // implicit-GEMM 3x3 convolution (conv_cpb > 0): A rows are NHWC pixels, K runs over (tap, 64-channel block);
+  // the A tile of a k-block is a 4-D TMA box [64 ch, w_box, h_box, 1] shifted by the tap, zero-filled outside.
+  int conv_cpb;       // Cin / 64 (0 = plain GEMM)
+  int conv_h, conv_w; // image height / width in pixels
 };
 
 constexpr int GEMM_BM = 128;
@@ -156,17 +160,40 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * GEMM_BM;
         const int n0 = (tile % n_tiles) * BN + int(cta_rank) * (BN / CTAS);
+        // implicit-GEMM conv: first pixel of this CTA's 128-row tile -> (image, y, x)
+        int cimg = 0, cy0 = 0, cx0 = 0;
+        if (ep.conv_cpb > 0) {
+          const int hw = ep.conv_h * ep.conv_w;
+          cimg = m0 / hw;
+          const int rem = m0 - cimg * hw;
+          cy0 = rem / ep.conv_w;
+          cx0 = rem - cy0 * ep.conv_w;
+        }
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          int tap = 0, cb = kb;
+          if (ep.conv_cpb > 0) {
+            tap = kb / ep.conv_cpb;
+            cb = kb - tap * ep.conv_cpb;
+          }
+          const int ky = tap / 3, kx = tap - 3 * ky;
           if constexpr (CTAS == 2) {
             // Only the leader arms its barrier (for both CTAs' bytes).  The peer may run at most one phase ahead:
             // its own empty barrier is released by the commit that follows the MMAs of the previous phase.
             if (leader) mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES * 2);
-            tma_load_2d_pair(smem_a + stage * S::A_BYTES, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
+            if (ep.conv_cpb > 0)
+              tma_load_4d_pair(smem_a + stage * S::A_BYTES, &tmap_a, &full_bar[stage], cb * GEMM_BK, cx0 + kx - 1,
+                               cy0 + ky - 1, cimg);
+            else
+              tma_load_2d_pair(smem_a + stage * S::A_BYTES, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
             tma_load_2d_pair(smem_b + stage * S::B_BYTES, &tmap_b, &full_bar[stage], kb * GEMM_BK, n0);
           } else {
             mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-            tma_load_2d(smem_a + stage * S::A_BYTES, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
+            if (ep.conv_cpb > 0)
+              tma_load_4d(smem_a + stage * S::A_BYTES, &tmap_a, &full_bar[stage], cb * GEMM_BK, cx0 + kx - 1,
+                          cy0 + ky - 1, cimg);
+            else
+              tma_load_2d(smem_a + stage * S::A_BYTES, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
             tma_load_2d(smem_b + stage * S::B_BYTES, &tmap_b, &full_bar[stage], kb * GEMM_BK, n0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }

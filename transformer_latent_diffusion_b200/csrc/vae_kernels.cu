@@ -210,6 +210,13 @@ __attribute__((visibility("default"))) int tld_vae_add_bias(const uint16_t* x, c
   return tld::launch_add_bias(reinterpret_cast<const tld::bf16*>(x), reinterpret_cast<const tld::bf16*>(h), bias,
                               reinterpret_cast<tld::bf16*>(out), numel, channels, reinterpret_cast<cudaStream_t>(stream));
 }
+__attribute__((visibility("default"))) int tld_vae_conv3x3(const uint16_t* x, const uint16_t* w, const float* bias,
+                                                           uint16_t* out, int batch, int h, int w_px, int cin, int cout,
+                                                           void* stream) {
+  return tld::launch_conv3x3(reinterpret_cast<const tld::bf16*>(x), reinterpret_cast<const tld::bf16*>(w), bias,
+                             reinterpret_cast<tld::bf16*>(out), batch, h, w_px, cin, cout,
+                             reinterpret_cast<cudaStream_t>(stream));
+}
 __attribute__((visibility("default"))) int tld_vae_upsample2x(const uint16_t* x, uint16_t* y, int batch, int h, int w,
                                                               int channels, void* stream) {
   return tld::launch_upsample2x(reinterpret_cast<const tld::bf16*>(x), reinterpret_cast<tld::bf16*>(y), batch, h, w,

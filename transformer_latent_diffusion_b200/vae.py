@@ -9,10 +9,11 @@ diffusers/SDXL-VAE structure with diffusers-compatible ``state_dict`` keys (``po
 fp32 restatement in ``oracle/vae_oracle.py`` with random weights.
 
 ROUND-1 STATUS: on CUDA/bf16 the GroupNorm(+SiLU) and nearest-2x upsample stages run on hand-written kernels
-(``csrc/vae_kernels.cu`` through ``tld_vae_group_norm`` / ``tld_vae_upsample2x``; in the stock ATen path they were 72 %
-of the decode time); the 3x3/1x1 convolutions and the single mid-block attention still run on PyTorch's library
-kernels (cuDNN implicit GEMM) -- the one part of the north-star path that is not yet hand-written sm_100a code (see
-DESIGN.md "VAE decode").  bench.py reports the denoiser-only number next to the end-to-end one.
+(``csrc/vae_kernels.cu`` through ``tld_vae_group_norm`` / ``tld_vae_upsample2x`` / ``tld_vae_add_bias``; in the stock
+ATen path they were 72 % of the decode time) and every 3x3 convolution with >= 64 channels (99.9 % of the decoder's
+FLOPs) runs as an implicit GEMM on the tcgen05 GEMM core (``tld_vae_conv3x3``: 4-D TMA boxes shifted per tap, zero
+fill = padding).  Still on PyTorch library kernels: conv_in (4 input channels), conv_out (3 output channels), the two
+1x1 shortcut convs, post_quant_conv and the single-head mid-block attention (together < 1 % of the FLOPs).
 """
 from __future__ import annotations
 
@@ -113,7 +114,34 @@ class AutoencoderKLDecoder(nn.Module):
         return mod._parameters[leaf]
 
     # -- building blocks ---------------------------------------------------------------------------------------
+    def _own_conv_ok(self, x, name) -> bool:
+        """3x3 conv eligible for the tcgen05 implicit-GEMM kernel (tld_vae_conv3x3)"""
+        w = self._p(name + ".weight")
+        cout, cin, kh, kw = w.shape
+        B, _, H, W = x.shape
+        wb = min(W, 128)
+        return (x.is_cuda and x.dtype == torch.bfloat16 and kh == 3 and kw == 3 and cin % 64 == 0 and cout % 64 == 0
+                and (H * W) % 128 == 0 and 128 % wb == 0 and W % wb == 0 and H % (128 // wb) == 0)
+
     def _conv(self, x, name, pad, bias=True):
+        if pad == 1 and self._own_conv_ok(x, name):
+            from . import _lib
+
+            w = self._p(name + ".weight")
+            cout, cin = w.shape[0], w.shape[1]
+            cache = self.__dict__.setdefault("_wpack_cache", {})
+            wp = cache.get(name)
+            if wp is None or wp.device != x.device:
+                # [Cout, Cin, 3, 3] -> [Cout, (ky, kx, cin)] bf16: the K order the implicit GEMM walks
+                wp = w.detach().permute(0, 2, 3, 1).reshape(cout, 9 * cin).to(torch.bfloat16).contiguous()
+                cache[name] = wp
+            x = x.contiguous(memory_format=torch.channels_last)
+            B, _, H, W = x.shape
+            y = torch.empty((B, cout, H, W), device=x.device, dtype=x.dtype).contiguous(memory_format=torch.channels_last)
+            bp = self._f32(name + ".bias", x.device).data_ptr() if bias else None
+            _lib.check(_lib.load().tld_vae_conv3x3(x.data_ptr(), wp.data_ptr(), bp, y.data_ptr(), B, H, W, cin, cout,
+                                                   _lib.current_stream_ptr(x.device)), "tld_vae_conv3x3")
+            return y
         return F.conv2d(x, self._p(name + ".weight"), self._p(name + ".bias") if bias else None, padding=pad)
 
     def _f32(self, key: str, device) -> torch.Tensor:
@@ -151,19 +179,19 @@ class AutoencoderKLDecoder(nn.Module):
         h = F.group_norm(x, GN_GROUPS, self._p(name + ".weight"), self._p(name + ".bias"), GN_EPS)
         return F.silu(h) if silu else h
 
-    def _add_bias(self, x, h, bias_of):
-        """x + h + bias (the skipped bias of conv `bias_of`)"""
+    def _add_bias(self, x, h, bias_of=None):
+        """x + h (+ the skipped bias of conv `bias_of`)"""
         if self._fusable(h) and x.shape == h.shape and x.dtype == h.dtype:
             from . import _lib
 
             x = x.contiguous(memory_format=torch.channels_last)
             h = h.contiguous(memory_format=torch.channels_last)
             out = torch.empty_like(h)
-            _lib.check(_lib.load().tld_vae_add_bias(x.data_ptr(), h.data_ptr(), self._f32(bias_of + ".bias", h.device).data_ptr(),
-                                                    out.data_ptr(), h.numel(), h.shape[1],
+            bp = self._f32(bias_of + ".bias", h.device).data_ptr() if bias_of else None
+            _lib.check(_lib.load().tld_vae_add_bias(x.data_ptr(), h.data_ptr(), bp, out.data_ptr(), h.numel(), h.shape[1],
                                                     _lib.current_stream_ptr(h.device)), "tld_vae_add_bias")
             return out
-        return x + h + self._p(bias_of + ".bias").view(1, -1, 1, 1)
+        return x + h + self._p(bias_of + ".bias").view(1, -1, 1, 1) if bias_of else x + h
 
     def _upsample2x(self, x):
         if x.is_cuda and x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0:
@@ -178,7 +206,14 @@ class AutoencoderKLDecoder(nn.Module):
         return F.interpolate(x, scale_factor=2.0, mode="nearest")
 
     def _resnet(self, x, name):
-        # conv biases are folded into the next fused kernel (GroupNorm input / residual add) instead of a separate pass
+        if self._own_conv_ok(x, name + ".conv1"):
+            # tcgen05 implicit-GEMM convs: the bias is part of the GEMM epilogue
+            h = self._conv(self._group_norm(x, name + ".norm1", True), name + ".conv1", 1)
+            h = self._conv(self._group_norm(h, name + ".norm2", True), name + ".conv2", 1)
+            if (name + ".conv_shortcut.weight") in self._layout:
+                x = self._conv(x, name + ".conv_shortcut", 0)
+            return self._add_bias(x, h)
+        # library convs: their biases are folded into the next fused kernel (GroupNorm input / residual add)
         h = self._conv(self._group_norm(x, name + ".norm1", True), name + ".conv1", 1, bias=False)
         h = self._conv(self._group_norm(h, name + ".norm2", True, pre_bias=name + ".conv1"), name + ".conv2", 1, bias=False)
         if (name + ".conv_shortcut.weight") in self._layout:
