@@ -95,6 +95,7 @@ class AutoencoderKLDecoder(nn.Module):
     def __init__(self, latent_ch: int = LATENT_CH, block_out: Tuple[int, ...] = BLOCK_OUT, chunk: int = 16):
         super().__init__()
         self.latent_ch, self.block_out, self.chunk = latent_ch, tuple(block_out), chunk
+        self.own_launches = 0  # libtld_b200 kernels launched by decode() so far (bench.py's gpu_launches)
         self._layout = vae_param_layout(latent_ch, block_out)
         for key, shape in self._layout.items():
             if key.endswith("weight") and len(shape) == 1:
@@ -137,10 +138,11 @@ class AutoencoderKLDecoder(nn.Module):
                 cache[name] = wp
             x = x.contiguous(memory_format=torch.channels_last)
             B, _, H, W = x.shape
-            y = torch.empty((B, cout, H, W), device=x.device, dtype=x.dtype).contiguous(memory_format=torch.channels_last)
+            y = torch.empty((B, cout, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
             bp = self._f32(name + ".bias", x.device).data_ptr() if bias else None
             _lib.check(_lib.load().tld_vae_conv3x3(x.data_ptr(), wp.data_ptr(), bp, y.data_ptr(), B, H, W, cin, cout,
                                                    _lib.current_stream_ptr(x.device)), "tld_vae_conv3x3")
+            self.own_launches += 1
             return y
         return F.conv2d(x, self._p(name + ".weight"), self._p(name + ".bias") if bias else None, padding=pad)
 
@@ -173,6 +175,7 @@ class AutoencoderKLDecoder(nn.Module):
                 x.data_ptr(), pb, self._f32(name + ".weight", x.device).data_ptr(),
                 self._f32(name + ".bias", x.device).data_ptr(), y.data_ptr(), x.shape[0], x.shape[2] * x.shape[3], Cc,
                 GN_GROUPS, GN_EPS, int(silu), _lib.current_stream_ptr(x.device)), "tld_vae_group_norm")
+            self.own_launches += 2  # statistics + apply
             return y
         if pre_bias:
             x = x + self._p(pre_bias + ".bias").view(1, -1, 1, 1)
@@ -190,6 +193,7 @@ class AutoencoderKLDecoder(nn.Module):
             bp = self._f32(bias_of + ".bias", h.device).data_ptr() if bias_of else None
             _lib.check(_lib.load().tld_vae_add_bias(x.data_ptr(), h.data_ptr(), bp, out.data_ptr(), h.numel(), h.shape[1],
                                                     _lib.current_stream_ptr(h.device)), "tld_vae_add_bias")
+            self.own_launches += 1
             return out
         return x + h + self._p(bias_of + ".bias").view(1, -1, 1, 1) if bias_of else x + h
 
@@ -199,9 +203,10 @@ class AutoencoderKLDecoder(nn.Module):
 
             x = x.contiguous(memory_format=torch.channels_last)
             B, Cc, H, W = x.shape
-            y = torch.empty((B, Cc, 2 * H, 2 * W), device=x.device, dtype=x.dtype).contiguous(memory_format=torch.channels_last)
+            y = torch.empty((B, Cc, 2 * H, 2 * W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
             _lib.check(_lib.load().tld_vae_upsample2x(x.data_ptr(), y.data_ptr(), B, H, W, Cc,
                                                       _lib.current_stream_ptr(x.device)), "tld_vae_upsample2x")
+            self.own_launches += 1
             return y
         return F.interpolate(x, scale_factor=2.0, mode="nearest")
 
