@@ -119,6 +119,29 @@ TLD_API int tld_vae_conv3x3(const uint16_t* x, const uint16_t* w, const float* b
 /* nearest-neighbour 2x upsample, NHWC bf16: x [batch,h,w,channels] -> y [batch,2h,2w,channels] */
 TLD_API int tld_vae_upsample2x(const uint16_t* x, uint16_t* y, int batch, int h, int w, int channels, void* stream);
 
+/* ---- backward-pass ops of the training step (autograd through tld/transformer_blocks.py:135-139, driven by
+ * tld/train.py:160-170), exported for the parity tests (tests/test_backward_gpu.py) ------------------------------
+ * in fp32 [rows,cols] -> out bf16 [rows,cols] (nullable) and outT bf16 [cols,rows] (nullable): operands of dgrad/wgrad */
+TLD_API int tld_bwd_cast_transpose(const float* in, uint16_t* out, uint16_t* outT, int rows, int cols, void* stream);
+/* out[c] = sum_r in[r,c] (bias gradients) */
+TLD_API int tld_bwd_colsum(const float* in, float* out, int rows, int cols, void* stream);
+/* LayerNorm backward: dx += dLN(dy; x, gamma); dgamma, dbeta [D] overwritten */
+TLD_API int tld_bwd_layernorm(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
+                              int rows, int D, void* stream);
+/* depthwise-3x3 + GELU backward (token grid NHWC bf16): hid = conv input, dg = grad of the GELU output ->
+ * dhid (grad of conv input), dw9 [9,C] tap-major, db [C]; du_tmp is a scratch buffer shaped like hid */
+TLD_API int tld_bwd_dwconv_gelu(const uint16_t* hid, const uint16_t* dg, const float* w9, const float* bias,
+                                uint16_t* du_tmp, uint16_t* dhid, float* dw9, float* db, int batch, int grid, int channels,
+                                void* stream);
+/* 2-key cross-attention backward: q bf16 [B*n_tok, D], go = d(out) fp32, kv0/kv1 [B, 2D] (K|V) -> dq bf16,
+ * dkv0/dkv1 [B, 2D] accumulated with atomicAdd (zero them first) */
+TLD_API int tld_bwd_xattn(const uint16_t* q, const float* go, const float* kv0, const float* kv1, uint16_t* dq, float* dkv0,
+                          float* dkv1, int batch, int n_tok, int D, void* stream);
+/* self-attention backward (n_tok <= 256): qkv bf16 [T,3D], d_out fp32 [T,D] (= residual gradient), x_before/x_after the
+ * residual stream around the attention (O = x_after - x_before) -> dqkv bf16 [T,3D] */
+TLD_API int tld_bwd_self_attention(const uint16_t* qkv, const float* d_out, const float* x_before, const float* x_after,
+                                   uint16_t* dqkv, int batch, int n_tok, int D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,66 +42,10 @@ __global__ void transpose_f32_kernel(const float* __restrict__ s, float* __restr
   }
 }
 
-enum PackKind { P_F32, P_BF16, P_TRANSPOSE_F32 };
-struct Slot {
-  PackKind kind;
-  void* dst;
-  long long numel;
-  int rows, cols;  // for P_TRANSPOSE_F32: source is [rows, cols]
-  bool filled;
-};
-
 }  // namespace tld
 
+#include "handle.h"
 using namespace tld;
-
-struct tld_denoiser {
-  tld_config cfg;
-  int device;
-  int D, L, N, G, pd, H4, E, Te, C, img, patch;
-  std::map<std::string, Slot> slots;
-  std::vector<void*> allocs;
-  float* staging = nullptr;
-  long long staging_elems = 0;
-
-  // parameters (device)
-  CondW cond;
-  EmbedW emb;
-  float *out_w, *out_b;
-  struct Layer {
-    bf16 *wqkv, *wq, *wup, *wdown;
-    float *ln1w, *ln1b, *ln2w, *ln2b, *ln3w, *ln3b, *bup, *dww9, *dwb, *bdown;
-  };
-  std::vector<Layer> layers;
-  bf16* wkv_all = nullptr;  // [L*2D, D]
-
-  // activation workspace, sized for ws_batch samples
-  int ws_batch = 0;
-  float* x_res = nullptr;   // [T, D] fp32 residual stream
-  bf16* xn = nullptr;       // [T, D]
-  bf16* qkv = nullptr;      // [T, 3D]
-  bf16* hid = nullptr;      // [T, 4D]
-  bf16* hid2 = nullptr;     // [T, 4D]
-  float* model_out = nullptr;  // [B, C, H, W]
-  // conditioning workspace
-  int ws_cond_rows = 0;
-  bf16* ycond = nullptr;    // [rows, D]
-  float* kv = nullptr;      // [rows, L*2D]
-  float* tlevels = nullptr; // [max steps]
-
-  // sampler state
-  cudaStream_t own_stream = nullptr;
-  cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
-  float *x_t = nullptr, *x0_prev = nullptr, *x0_out = nullptr;
-  int sampler_batch = 0;
-  StepCoef* step_table = nullptr;
-  int step_table_cap = 0;
-  int* step_ptr = nullptr;
-  cudaGraphExec_t graph_exec = nullptr;
-  int graph_batch = -1;
-  float last_loop_ms = 0.f;
-  long long last_launches = 0;
-};
 
 namespace tld {
 

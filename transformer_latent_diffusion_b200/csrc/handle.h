@@ -1,0 +1,95 @@
+// The library handle shared by api.cu (inference) and train.cu (training step).
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/tld_b200.h"
+#include "common.h"
+
+namespace tld {
+
+enum PackKind { P_F32, P_BF16, P_TRANSPOSE_F32 };
+struct Slot {
+  PackKind kind;
+  void* dst;
+  long long numel;
+  int rows, cols;  // for P_TRANSPOSE_F32: source is [rows, cols]
+  bool filled;
+};
+
+}  // namespace tld
+
+using namespace tld;  // internal header: the handle is the C-ABI opaque type and lives in the global namespace
+
+struct tld_denoiser {
+  tld_config cfg;
+  int device;
+  int D, L, N, G, pd, H4, E, Te, C, img, patch;
+  std::map<std::string, Slot> slots;
+  std::vector<void*> allocs;
+  float* staging = nullptr;
+  long long staging_elems = 0;
+
+  // parameters (device)
+  CondW cond;
+  EmbedW emb;
+  float *out_w, *out_b;
+  struct Layer {
+    bf16 *wqkv, *wq, *wup, *wdown;
+    float *ln1w, *ln1b, *ln2w, *ln2b, *ln3w, *ln3b, *bup, *dww9, *dwb, *bdown;
+  };
+  std::vector<Layer> layers;
+  bf16* wkv_all = nullptr;  // [L*2D, D]
+
+  // activation workspace, sized for ws_batch samples
+  int ws_batch = 0;
+  float* x_res = nullptr;   // [T, D] fp32 residual stream
+  bf16* xn = nullptr;       // [T, D]
+  bf16* qkv = nullptr;      // [T, 3D]
+  bf16* hid = nullptr;      // [T, 4D]
+  bf16* hid2 = nullptr;     // [T, 4D]
+  float* model_out = nullptr;  // [B, C, H, W]
+  // conditioning workspace
+  int ws_cond_rows = 0;
+  bf16* ycond = nullptr;    // [rows, D]
+  float* kv = nullptr;      // [rows, L*2D]
+  float* tlevels = nullptr; // [max steps]
+
+  // sampler state
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  float *x_t = nullptr, *x0_prev = nullptr, *x0_out = nullptr;
+  int sampler_batch = 0;
+  StepCoef* step_table = nullptr;
+  int step_table_cap = 0;
+  int* step_ptr = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_batch = -1;
+  float last_loop_ms = 0.f;
+  long long last_launches = 0;
+
+  // ---- training step (train.cu) ----
+  struct TrainLayer {
+    float *xs0, *xs1, *xs2;        // residual stream before self-attn / cross-attn / MLP, fp32 [T,D]
+    bf16 *qkv, *hid, *hid2;        // saved GEMM outputs
+  };
+  struct TrainWeightsT {           // transposed bf16 copies for dgrad (refreshed by tld_denoiser_set_param)
+    bf16 *wqkvT, *wqT, *wupT, *wdownT;
+  };
+  std::vector<TrainLayer> tl;
+  std::vector<TrainWeightsT> wT;
+  bf16* wkv_allT = nullptr;        // [D, L*2D]
+  int train_batch = 0;
+  std::vector<void*> train_allocs;
+  std::map<std::string, std::pair<float*, long long>> grads;  // reference-layout fp32 gradient of every parameter
+  float* grad_arena = nullptr;
+  long long grad_elems = 0;
+  // scratch (sized with train_batch)
+  float *t_dx = nullptr, *t_dxn = nullptr, *t_xfinal = nullptr;
+  bf16 *t_a = nullptr, *t_aT = nullptr, *t_big = nullptr, *t_bigT = nullptr, *t_big2 = nullptr, *t_xnT = nullptr, *t_q = nullptr;
+  float *t_dkv = nullptr, *t_cond_pre = nullptr, *t_cond_h1 = nullptr, *t_cond_a1 = nullptr, *t_cond_emb = nullptr;
+  float *t_small = nullptr;
+};
+
+
