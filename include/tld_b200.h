@@ -119,6 +119,15 @@ TLD_API int tld_vae_conv3x3(const uint16_t* x, const uint16_t* w, const float* b
 /* nearest-neighbour 2x upsample, NHWC bf16: x [batch,h,w,channels] -> y [batch,2h,2w,channels] */
 TLD_API int tld_vae_upsample2x(const uint16_t* x, uint16_t* y, int batch, int h, int w, int channels, void* stream);
 
+/* ---- training step (tld/train.py:160-170: pred = model(x_noisy, sigma, label); loss.backward()) ---------------
+ * tld_train_forward == tld_denoiser_forward but keeps the activations; tld_train_backward turns d(loss)/d(pred) into
+ * the fp32 gradient of every parameter, read back per reference state_dict key with tld_train_get_grad (the caller
+ * owns loss, optimiser, EMA and the data-parallel all-reduce, exactly as in the reference).  <= 256 tokens/sample. */
+TLD_API int tld_train_forward(tld_denoiser* h, const float* x, const float* noise_level, const float* label, float* out,
+                              int batch, void* stream);
+TLD_API int tld_train_backward(tld_denoiser* h, const float* d_pred, int batch, void* stream);
+TLD_API int tld_train_get_grad(tld_denoiser* h, const char* key, float* dst, int64_t numel, void* stream);
+
 /* ---- backward-pass ops of the training step (autograd through tld/transformer_blocks.py:135-139, driven by
  * tld/train.py:160-170), exported for the parity tests (tests/test_backward_gpu.py) ------------------------------
  * in fp32 [rows,cols] -> out bf16 [rows,cols] (nullable) and outT bf16 [cols,rows] (nullable): operands of dgrad/wgrad */

@@ -1,0 +1,96 @@
+"""Training step on the GPU: gradients of every parameter through the C ABI (tld_train_forward/backward) against
+autograd through the oracle (fp32, CPU), then two Adam steps against the oracle's two steps.
+
+Tolerance: bf16 tensor-core operands (activations, gradients, weights) with fp32 accumulation vs a pure fp32 oracle:
+per-parameter rel-Fro <= 5e-2, typically 1e-2."""
+import pytest
+import torch
+
+from conftest import rel_fro
+from oracle import tld_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_grads(cfg, sd, x, t, lab, target):
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and not k.endswith("angular_speeds")}
+    live = dict(sd)
+    live.update(params)
+    pred = O.denoiser_forward(live, cfg, x, t, lab)
+    loss = torch.nn.functional.mse_loss(pred, target)
+    loss.backward()
+    return float(loss), {k: p.grad for k, p in params.items()}, pred.detach()
+
+
+def _model(cfg, sd):
+    from transformer_latent_diffusion_b200.denoiser import Denoiser
+
+    m = Denoiser(cfg.image_size, cfg.noise_embed_dims, cfg.patch_size, cfg.embed_dim, cfg.dropout, cfg.n_layers,
+                 cfg.text_emb_size, cfg.mlp_multiplier, cfg.n_channels)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().train()
+
+
+@pytest.mark.parametrize("img,D,L,B", [(16, 128, 2, 4), (32, 256, 1, 3), (32, 768, 2, 2)])
+def test_parameter_gradients_match_oracle(img, D, L, B):
+    cfg = O.OracleCfg(image_size=img, embed_dim=D, n_layers=L)
+    sd = O.synth_state_dict(cfg, 17)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, 4, img, img, generator=g)
+    t = torch.rand(B, 1, generator=g)
+    lab = torch.randn(B, 768, generator=g)
+    lab[1] = 0  # a dropped label
+    target = torch.randn(B, 4, img, img, generator=g)
+    loss_ref, gref, pred_ref = _oracle_grads(cfg, sd, x, t, lab, target)
+    m = _model(cfg, sd)
+    pred = m(x.cuda(), t.cuda(), lab.cuda())
+    assert pred.requires_grad and rel_fro(pred, pred_ref) < 1e-2
+    loss = torch.nn.functional.mse_loss(pred, target.cuda())
+    loss.backward()
+    assert abs(float(loss) - loss_ref) < 2e-2 * abs(loss_ref)
+    worst = []
+    for k, p in m.named_parameters():
+        assert p.grad is not None and p.grad.shape == p.shape, k
+        worst.append((rel_fro(p.grad, gref[k]), k))
+    worst.sort(reverse=True)
+    assert worst[0][0] < 5e-2, worst[:6]
+
+
+def test_two_adam_steps_follow_oracle():
+    from transformer_latent_diffusion_b200.train import noise_batch, train_step, update_ema
+    import copy
+
+    cfg = O.OracleCfg(image_size=16, embed_dim=128, n_layers=2)
+    sd = O.synth_state_dict(cfg, 23)
+    m = _model(cfg, sd)
+    ema = copy.deepcopy(m)
+    opt = torch.optim.Adam(m.parameters(), lr=3e-4)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and not k.endswith("angular_speeds")}
+    live = dict(sd)
+    live.update(params)
+    opt_ref = torch.optim.Adam(list(params.values()), lr=3e-4)
+    g = torch.Generator().manual_seed(9)
+    for step in range(2):
+        x = torch.randn(6, 4, 16, 16, generator=g) * 8
+        y = torch.randn(6, 768, generator=g)
+        sigma = torch.rand(6, generator=g, dtype=torch.float64)
+        eps = torch.randn(6, 4, 16, 16, generator=g)
+        mask = torch.rand(6, generator=g) < 0.3
+        xs, xn, sg, lab = O.noise_inputs(x, sigma, eps, y, mask)
+        opt_ref.zero_grad()
+        loss_ref = torch.nn.functional.mse_loss(O.denoiser_forward(live, cfg, xn, sg, lab), xs)
+        loss_ref.backward()
+        opt_ref.step()
+        a, b, c, d = noise_batch(x.cuda(), y.cuda(), sigma.cuda(), eps.cuda(), mask.cuda(), 8.0)
+        assert torch.allclose(b.cpu(), xn, atol=1e-6)
+        loss = train_step(m, opt, a, b, c, d)
+        update_ema(ema, m, 0.999)
+        assert abs(float(loss) - float(loss_ref)) < 2e-2 * float(loss_ref), (step, float(loss), float(loss_ref))
+    # after two Adam steps the weights moved by ~2*lr in the sign direction of the gradient: compare the updates
+    k = "denoiser_trans_block.decoder_blocks.1.mlp.mlp.0.weight"
+    mine = dict(m.named_parameters())[k].detach().cpu() - sd[k]
+    ref = params[k].detach() - sd[k]
+    assert rel_fro(mine, ref) < 0.15
+    # EMA after two updates: e2 = a^2 w0 + a(1-a) w1 + (1-a) w2  (tld/train.py:55-58)
+    e = dict(ema.named_parameters())[k].detach().cpu()
+    assert (e - sd[k]).abs().max() < 2.1e-3 * 6e-4 + 1e-7  # |ema - w0| <= (1-a)(|w1-w0| + |w2-w0|) ~ 1e-3 * 3 lr

@@ -179,6 +179,12 @@ static int ensure_cond(tld_denoiser* h, int rows) {
   return 0;
 }
 
+}  // namespace tld
+int tld_internal_ensure(tld_denoiser* h, int batch, int cond_rows) {
+  return tld::ensure_workspace(h, batch) || tld::ensure_cond(h, cond_rows);
+}
+namespace tld {
+
 static int g_attention_impl = 0;  // tld_set_option("attention_impl", ...)
 
 // The L decoder blocks + output projection on the tokens already in h->x_res (transformer_blocks.py:135-139).

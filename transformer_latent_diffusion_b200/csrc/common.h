@@ -55,9 +55,15 @@ struct EmbedW {
   const float* ln2_b;
   const float* pos;     // [N, D]
 };
+struct EmbedSave {  // optional fp32 intermediates kept for the backward pass (training)
+  float* u;    // [T, pd] gathered patch
+  float* c16;  // [T, pd] conv output (pre-LN)
+  float* t16;  // [T, pd] LN(pd) output
+  float* e;    // [T, D]  Linear(pd->D) output (pre-LN)
+};
 // x[Bx,C,H,W] fp32 -> tokens[Bout,N,D] fp32; sample b reads image b % Bx (CFG duplication)
 int launch_embed(const float* x, int Bx, int Bout, int C, int img, int patch, int D, const EmbedW& w, float* out,
-                 cudaStream_t st);
+                 cudaStream_t st, const EmbedSave* sv = nullptr);
 struct CondW {
   const float* speeds;  // [E/2]
   const float* w1;      // [D, E]
@@ -69,11 +75,18 @@ struct CondW {
   const float* ln_w;    // [D]
   const float* ln_b;
 };
+struct CondSave {  // optional fp32 intermediates kept for the backward pass (training)
+  float* emb;  // [R, E]  sinusoidal features
+  float* a1;   // [R, D]  W1 emb + b1 (pre-GELU)
+  float* h1;   // [R, D]  gelu(a1)
+  float* pre;  // [R, D]  W2 h1 + b2 (pre-LayerNorm)
+};
 // noise token: y[r] = LN(W2 gelu(W1 sincos(t[r]) + b1) + b2)  -> bf16 [R, D]
-int launch_cond_noise(const float* t, int R, int E, int D, const CondW& w, bf16* y, cudaStream_t st);
+int launch_cond_noise(const float* t, int R, int E, int D, const CondW& w, bf16* y, cudaStream_t st,
+                      const CondSave* sv = nullptr);
 // label token: y[r] = LN(Wl label[r] + bl); label == nullptr or r >= R_real -> zero label (uncond half)
 int launch_cond_label(const float* label, int R, int R_real, int Te, int D, const CondW& w, bf16* y,
-                      cudaStream_t st);
+                      cudaStream_t st, float* pre_save = nullptr);
 // g = gelu(dwconv3x3(h) + b) over the token grid; h,g bf16 [B, grid, grid, C]; w tap-major [9, C]
 int launch_dwconv_gelu(const bf16* h, const float* w9, const float* bias, bf16* g, int B, int grid, int C,
                        cudaStream_t st);

@@ -92,4 +92,5 @@ struct tld_denoiser {
   float *t_small = nullptr;
 };
 
-
+// api.cu: (re)allocate the inference workspaces for `batch` samples and `cond_rows` conditioning rows
+int tld_internal_ensure(tld_denoiser* h, int batch, int cond_rows);

@@ -84,7 +84,7 @@ int launch_layernorm_bf16(const float* x, const float* gamma, const float* beta,
 // --------------------------------------------------------------------------------------------
 template <int V>
 __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ x, int Bx, int Bout, int C, int img,
-                                                    int patch, EmbedW w, float* __restrict__ out) {
+                                                    int patch, EmbedW w, float* __restrict__ out, EmbedSave sv) {
   constexpr int D = V * 128;
   __shared__ float s_t[8][64];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -101,6 +101,8 @@ __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ x,
     t[i] = xb[(size_t)c * img * img + (size_t)(gy * patch + p1) * img + gx * patch + p2];
   }
   __syncwarp();
+  if (sv.u)
+    for (int i = lane; i < pd; i += 32) sv.u[(size_t)tok * pd + i] = t[i];
   float conv[2] = {0.f, 0.f};
   float s = 0.f;
 #pragma unroll
@@ -123,7 +125,13 @@ __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ x,
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int o = lane + 32 * r;
-    if (o < pd) t[o] = (conv[r] - mu1) * rstd1 * w.ln1_w[o] + w.ln1_b[o];
+    if (o < pd) {
+      t[o] = (conv[r] - mu1) * rstd1 * w.ln1_w[o] + w.ln1_b[o];
+      if (sv.c16) {
+        sv.c16[(size_t)tok * pd + o] = conv[r];
+        sv.t16[(size_t)tok * pd + o] = t[o];
+      }
+    }
   }
   __syncwarp();
   // Linear pd -> D with the transposed weight [pd, D] (coalesced float4 per lane)
@@ -141,6 +149,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ x,
       acc.w += wv.w * ti;
     }
     e[j] = acc;
+    if (sv.e) reinterpret_cast<float4*>(sv.e + (size_t)tok * D)[lane + 32 * j] = acc;
     s2 += (acc.x + acc.y) + (acc.z + acc.w);
   }
   const float mu2 = warp_sum(s2) * (1.0f / D);
@@ -168,7 +177,8 @@ __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ x,
 }
 
 int launch_embed(const float* x, int Bx, int Bout, int C, int img, int patch, int D, const EmbedW& w, float* out,
-                 cudaStream_t st) {
+                 cudaStream_t st, const EmbedSave* svp) {
+  const EmbedSave sv = svp ? *svp : EmbedSave{nullptr, nullptr, nullptr, nullptr};
   TLD_CHECK(D % 128 == 0 && D >= 128 && D <= 1024, "embed: embed_dim must be a multiple of 128 in [128,1024]");
   TLD_CHECK(C * patch * patch <= 64, "embed: patch_dim (n_channels*patch^2) must be <= 64");
   TLD_CHECK(img % patch == 0, "embed: image_size must be divisible by patch_size");
@@ -176,7 +186,7 @@ int launch_embed(const float* x, int Bx, int Bout, int C, int img, int patch, in
   const int grid = int((toks + 7) / 8);
   switch (D / 128) {
 #define EM_CASE(V) \
-  case V: embed_kernel<V><<<grid, 256, 0, st>>>(x, Bx, Bout, C, img, patch, w, out); break;
+  case V: embed_kernel<V><<<grid, 256, 0, st>>>(x, Bx, Bout, C, img, patch, w, out, sv); break;
     EM_CASE(1) EM_CASE(2) EM_CASE(3) EM_CASE(4) EM_CASE(5) EM_CASE(6) EM_CASE(7) EM_CASE(8)
 #undef EM_CASE
   }
@@ -190,7 +200,7 @@ int launch_embed(const float* x, int Bx, int Bout, int C, int img, int patch, in
 // Dense layers: one warp per output feature, lanes stride the (coalesced) weight row, warp reduce.
 // --------------------------------------------------------------------------------------------
 __device__ void block_dense(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ in,
-                            float* __restrict__ outv, int n_out, int n_in, bool gelu) {
+                            float* __restrict__ outv, int n_out, int n_in, bool gelu, float* __restrict__ pre_out = nullptr) {
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int o = wib; o < n_out; o += nw) {
     const float* wr = W + (size_t)o * n_in;
@@ -199,6 +209,7 @@ __device__ void block_dense(const float* __restrict__ W, const float* __restrict
     acc = warp_sum(acc);
     if (lane == 0) {
       acc += bias[o];
+      if (pre_out) pre_out[o] = acc;
       outv[o] = gelu ? gelu_erf(acc) : acc;
     }
   }
@@ -229,7 +240,7 @@ __device__ void block_layernorm_store(const float* __restrict__ v, const float* 
 }
 
 __global__ void __launch_bounds__(256) cond_noise_kernel(const float* __restrict__ t, int E, int D, CondW w,
-                                                         bf16* __restrict__ y) {
+                                                         bf16* __restrict__ y, CondSave sv) {
   extern __shared__ float sm[];  // [E] sincos | [D] h1 | [D] h2 | [8] red
   float* emb = sm;
   float* h1 = sm + E;
@@ -243,13 +254,20 @@ __global__ void __launch_bounds__(256) cond_noise_kernel(const float* __restrict
     emb[E / 2 + i] = cosf(a);
   }
   __syncthreads();
-  block_dense(w.w1, w.b1, emb, h1, D, E, true);
+  block_dense(w.w1, w.b1, emb, h1, D, E, true, sv.a1 ? sv.a1 + (size_t)r * D : nullptr);
   block_dense(w.w2, w.b2, h1, h2, D, D, false);
+  if (sv.emb) {  // training: keep what the backward pass needs
+    for (int i = threadIdx.x; i < E; i += blockDim.x) sv.emb[(size_t)r * E + i] = emb[i];
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      sv.h1[(size_t)r * D + i] = h1[i];
+      sv.pre[(size_t)r * D + i] = h2[i];
+    }
+  }
   block_layernorm_store(h2, w.ln_w, w.ln_b, y + (size_t)r * D, D, red);
 }
 
 __global__ void __launch_bounds__(256) cond_label_kernel(const float* __restrict__ label, int R_real, int Te, int D,
-                                                         CondW w, bf16* __restrict__ y) {
+                                                         CondW w, bf16* __restrict__ y, float* __restrict__ pre_save) {
   extern __shared__ float sm[];  // [Te] label | [D] proj | [8] red
   float* lab = sm;
   float* proj = sm + Te;
@@ -259,21 +277,23 @@ __global__ void __launch_bounds__(256) cond_label_kernel(const float* __restrict
   for (int i = threadIdx.x; i < Te; i += blockDim.x) lab[i] = real ? label[(size_t)r * Te + i] : 0.f;
   __syncthreads();
   block_dense(w.wl, w.bl, lab, proj, D, Te, false);
+  if (pre_save)
+    for (int i = threadIdx.x; i < D; i += blockDim.x) pre_save[(size_t)r * D + i] = proj[i];
   block_layernorm_store(proj, w.ln_w, w.ln_b, y + (size_t)r * D, D, red);
 }
 
-int launch_cond_noise(const float* t, int R, int E, int D, const CondW& w, bf16* y, cudaStream_t st) {
+int launch_cond_noise(const float* t, int R, int E, int D, const CondW& w, bf16* y, cudaStream_t st, const CondSave* sv) {
   if (R <= 0) return 0;
   const size_t smem = (size_t)(E + 2 * D + 8) * sizeof(float);
-  cond_noise_kernel<<<R, 256, smem, st>>>(t, E, D, w, y);
+  cond_noise_kernel<<<R, 256, smem, st>>>(t, E, D, w, y, sv ? *sv : CondSave{nullptr, nullptr, nullptr, nullptr});
   TLD_CUDA_OK(cudaGetLastError());
   return 0;
 }
 int launch_cond_label(const float* label, int R, int R_real, int Te, int D, const CondW& w, bf16* y,
-                      cudaStream_t st) {
+                      cudaStream_t st, float* pre_save) {
   if (R <= 0) return 0;
   const size_t smem = (size_t)(Te + D + 8) * sizeof(float);
-  cond_label_kernel<<<R, 256, smem, st>>>(label, R_real, Te, D, w, y);
+  cond_label_kernel<<<R, 256, smem, st>>>(label, R_real, Te, D, w, y, pre_save);
   TLD_CUDA_OK(cudaGetLastError());
   return 0;
 }

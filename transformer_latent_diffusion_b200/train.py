@@ -1,0 +1,167 @@
+"""Training step — drop-in for ``tld.train`` on the hot path (reference tld/train.py).
+
+* ``denoiser_autograd_forward`` makes ``Denoiser.forward`` differentiable: forward = ``tld_train_forward`` (keeps the
+  activations in library-owned buffers), backward = ``tld_train_backward`` (tcgen05 dgrad/wgrad GEMMs + the backward
+  kernels of ``csrc/backward.cu`` / ``attention_bwd.cu``), gradients handed to autograd per parameter, so the caller's
+  optimiser / EMA / gradient clipping code is unchanged.
+* ``main(config)`` mirrors ``tld.train.main`` (tld/train.py:62-176): Beta(1,2.5) noise levels, linear-interp noising,
+  15 % label dropout, MSE against the clean latent, Adam(lr), EMA(alpha) on rank 0.  ``accelerate``/``wandb`` are not
+  available offline: the data-parallel part is plain ``torch.distributed`` (one process per GPU, NCCL all-reduce of
+  the flattened gradients = what DDP does inside ``accelerator.backward``), logging goes to stdout.
+  bf16 tensor-core operands with fp32 accumulation/master weights replace the reference's fp16 autocast + GradScaler
+  (no loss scaling needed).
+"""
+from __future__ import annotations
+
+import copy
+from dataclasses import asdict
+from typing import Optional
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+
+from . import _lib
+from .configs import ModelConfig
+
+
+class _DenoiserFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, x, noise_level, label, *params):
+        B = x.shape[0]
+        h = module._ensure_handle(x.device)
+        xf = x.detach().to(torch.float32).contiguous()
+        tf = noise_level.detach().to(device=x.device, dtype=torch.float32).reshape(B).contiguous()
+        lf = label.detach().to(device=x.device, dtype=torch.float32).contiguous()
+        out = torch.empty_like(xf)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().tld_train_forward(h, _lib.ptr(xf), _lib.ptr(tf), _lib.ptr(lf), _lib.ptr(out), B,
+                                                     _lib.current_stream_ptr(x.device)), "tld_train_forward")
+        ctx.module, ctx.batch, ctx.handle = module, B, h
+        ctx.keys = [k for k, _ in module.named_parameters()]
+        ctx.meta = [(p.shape, p.dtype) for p in params]
+        return out.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        dev = d_out.device
+        g = d_out.detach().to(torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            st = _lib.current_stream_ptr(dev)
+            _lib.check(lib.tld_train_backward(ctx.handle, _lib.ptr(g), ctx.batch, st), "tld_train_backward")
+            grads = []
+            for key, (shape, dtype) in zip(ctx.keys, ctx.meta):
+                t = torch.empty(shape, device=dev, dtype=torch.float32)
+                _lib.check(lib.tld_train_get_grad(ctx.handle, key.encode(), _lib.ptr(t), t.numel(), st), f"get_grad({key})")
+                grads.append(t if dtype == torch.float32 else t.to(dtype))
+        return (None, None, None, None, *grads)
+
+
+def denoiser_autograd_forward(module, x: Tensor, noise_level: Tensor, label: Tensor) -> Tensor:
+    """Differentiable ``Denoiser.forward`` (w.r.t. the parameters; the latents/labels get no gradient)."""
+    if module.image_size // module.patch_size > 16:
+        raise _lib.TldError("training path supports up to 256 tokens per sample (image_size/patch_size <= 16)")
+    params = [p for _, p in module.named_parameters()]
+    return _DenoiserFn.apply(module, x, noise_level, label, *params)
+
+
+def count_parameters(model: nn.Module) -> int:
+    return sum(p.numel() for p in model.parameters() if p.requires_grad)
+
+
+def count_parameters_per_layer(model: nn.Module) -> None:
+    for name, param in model.named_parameters():
+        print(f"{name}: {param.numel()} parameters")
+
+
+def update_ema(ema_model: nn.Module, model: nn.Module, alpha: float = 0.999) -> None:
+    """ema = alpha * ema + (1 - alpha) * param (tld/train.py:55-58), one fused foreach pass"""
+    with torch.no_grad():
+        ema_p = [p.data for p in ema_model.parameters()]
+        cur_p = [p.data for p in model.parameters()]
+        torch._foreach_mul_(ema_p, alpha)
+        torch._foreach_add_(ema_p, cur_p, alpha=1 - alpha)
+
+
+def noise_batch(x: Tensor, y: Tensor, noise_level: Tensor, noise: Tensor, drop_mask: Tensor, vae_scale_factor: float):
+    """tld/train.py:122-138 with the random draws passed in: returns (clean target, noisy input, sigma[B,1], labels)."""
+    x = x / vae_scale_factor
+    s = noise_level.double().view(-1, 1, 1, 1)
+    x_noisy = (s * noise.double() + (1 - s) * x.double()).float()
+    label = y.clone()
+    label[drop_mask] = 0
+    return x, x_noisy, noise_level.float().view(-1, 1), label
+
+
+def allreduce_gradients(model: nn.Module) -> None:
+    """Average the gradients over the data-parallel ranks with ONE flattened NCCL all-reduce (what DDP does in
+    accelerator.backward, tld/train.py:169); no-op without an initialised process group."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    flat = torch._utils._flatten_dense_tensors(grads)
+    dist.all_reduce(flat)
+    flat.div_(dist.get_world_size())
+    for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+        g.copy_(f)
+
+
+def train_step(model: nn.Module, optimizer, x: Tensor, x_noisy: Tensor, sigma: Tensor, label: Tensor) -> Tensor:
+    """zero_grad -> forward -> MSE -> backward -> (all-reduce) -> step (tld/train.py:160-170). Returns the loss tensor."""
+    model.train()
+    optimizer.zero_grad()
+    pred = model(x_noisy, sigma, label)
+    loss = torch.nn.functional.mse_loss(pred, x)
+    loss.backward()
+    allreduce_gradients(model)
+    optimizer.step()
+    return loss.detach()
+
+
+def main(config: ModelConfig, device: Optional[torch.device] = None, log_every: int = 50) -> nn.Module:
+    """Training loop with the reference's semantics (tld/train.py:62-176). Returns the EMA model (rank 0) / model."""
+    import torch.distributed as dist
+
+    from .denoiser import Denoiser
+
+    denoiser_config, train_config, dataconfig = config.denoiser_config, config.train_config, config.data_config
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    device = device or torch.device("cuda", torch.cuda.current_device())
+
+    latent_train_data = torch.tensor(np.load(dataconfig.latent_path), dtype=torch.float32)
+    train_label_embeddings = torch.tensor(np.load(dataconfig.text_emb_path), dtype=torch.float32)
+    n = latent_train_data.shape[0]
+    model = Denoiser(**asdict(denoiser_config)).to(device)
+    if world > 1:  # identical initial weights on every rank (DDP broadcasts rank 0's)
+        for p in model.parameters():
+            dist.broadcast(p.data, src=0)
+    optimizer = torch.optim.Adam(model.parameters(), lr=train_config.lr)
+    ema_model = copy.deepcopy(model) if rank == 0 else None
+    if rank == 0:
+        print(count_parameters(model))
+    global_step = 0
+    gen = torch.Generator().manual_seed(1234 + rank)
+    for epoch in range(1, train_config.n_epoch + 1):
+        perm = torch.randperm(n, generator=torch.Generator().manual_seed(epoch))  # same shuffle on every rank
+        shard = perm[rank::world]
+        for i in range(0, len(shard), train_config.batch_size):
+            idx = shard[i:i + train_config.batch_size]
+            x, y = latent_train_data[idx].to(device), train_label_embeddings[idx].to(device)
+            noise_level = torch.tensor(np.random.beta(train_config.beta_a, train_config.beta_b, len(x)), device=device)
+            noise = torch.randn(x.shape, generator=gen).to(device)
+            mask = (torch.rand(y.size(0), generator=gen) < 0.15).to(device)
+            xs, x_noisy, sigma, label = noise_batch(x, y, noise_level, noise, mask, config.vae_cfg.vae_scale_factor)
+            loss = train_step(model, optimizer, xs, x_noisy, sigma, label)
+            if rank == 0:
+                update_ema(ema_model, model, alpha=train_config.alpha)
+                if global_step % log_every == 0:
+                    print(f"epoch {epoch} step {global_step} train_loss {float(loss):.5f}")
+                if train_config.save_model and train_config.model_name and global_step % train_config.save_and_eval_every_iters == 0:
+                    torch.save({"model_ema": ema_model.state_dict(), "opt_state": optimizer.state_dict(),
+                                "global_step": global_step}, train_config.model_name)
+            global_step += 1
+    return ema_model if rank == 0 else model
