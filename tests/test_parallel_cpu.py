@@ -59,3 +59,34 @@ def test_generate_sharded_gloo_world2(tmp_path, n_imgs):
     mp.spawn(_worker, args=(2, port, n_imgs, out), nprocs=2, join=True)
     res, ref = torch.load(out)
     assert torch.equal(res, ref)
+
+
+def _grad_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    from transformer_latent_diffusion_b200.train import allreduce_gradients
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.LayerNorm(7), torch.nn.Linear(7, 3))
+    for i, p in enumerate(m.parameters()):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    allreduce_gradients(m)
+    if rank == 0:
+        torch.save([p.grad.clone() for p in m.parameters()], out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_allreduce_gradients_gloo_world2(tmp_path):
+    """the data-parallel gradient average of the training step (tld/train.py:169 via DDP) on 2 CPU ranks"""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "g.pt")
+    mp.spawn(_grad_worker, args=(2, port, out), nprocs=2, join=True)
+    grads = torch.load(out)
+    for i, g in enumerate(grads):
+        assert torch.allclose(g, torch.full_like(g, 1.5 * (i + 1)))  # mean of (1, 2) * (i + 1)
