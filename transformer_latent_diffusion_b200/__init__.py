@@ -27,5 +27,5 @@ def install_as_tld() -> None:
     if cur is not None and cur is not me:
         raise RuntimeError("another module named 'tld' is already imported")
     sys.modules["tld"] = me
-    for sub in ("configs", "denoiser", "diffusion"):
+    for sub in ("configs", "denoiser", "diffusion", "train"):
         sys.modules[f"tld.{sub}"] = importlib.import_module(f"{__name__}.{sub}")
