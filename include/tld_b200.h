@@ -49,7 +49,8 @@ typedef struct tld_config {
 TLD_API const char* tld_last_error(void);
 TLD_API int tld_version(void);
 /* Process-wide tuning switches (tests / experiments): "gemm_ctas" = 0 auto | 1 single-CTA tiles | 2 CTA-pair
- * (cta_group::2) tiles;  "attention_impl" = 0 auto | 1 mma.sync kernel | 2 tcgen05 kernel. */
+ * (cta_group::2) tiles;  "attention_impl" = 0 auto | 1 mma.sync kernel | 2 tcgen05 kernel;  "pdl" = 1 launch
+ * the step kernels with programmatic dependent launch (prologues overlap the previous kernel's tail) | 0 plain launches (default: measured no gain). */
 TLD_API int tld_set_option(const char* key, int value);
 
 /* ---- lifetime --------------------------------------------------------------------------------

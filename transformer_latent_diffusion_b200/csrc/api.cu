@@ -9,6 +9,7 @@
 #include "../../include/tld_b200.h"
 #include "common.h"
 #include "gemm_tcgen05.cuh"  // EpiMode
+#include "launch.h"
 
 namespace tld {
 
@@ -18,6 +19,10 @@ int fail(const std::string& msg) {
   return 1;
 }
 const char* last_error() { return g_err.c_str(); }
+
+static int g_pdl = 0;  // measured on B200: no gain (the step is power-capped, not launch-gap bound); kept as an option
+void set_pdl(int v) { g_pdl = v; }
+bool pdl_enabled() { return g_pdl != 0; }
 
 int sm_count() {
   static int n = 0;
@@ -235,6 +240,10 @@ int tld_set_option(const char* key, int value) {
   if (k == "gemm_ctas") {
     TLD_CHECK(value >= 0 && value <= 2, "gemm_ctas must be 0, 1 or 2");
     set_gemm_ctas(value);
+    return 0;
+  }
+  if (k == "pdl") {
+    set_pdl(value != 0);
     return 0;
   }
   if (k == "attention_impl") {

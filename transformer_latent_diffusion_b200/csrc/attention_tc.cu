@@ -12,6 +12,7 @@
 // Warps 0..3: softmax + epilogue (TMEM lane quarter = warp id).  Warp 4: TMEM alloc, TMA loads, MMA issue.
 // 80 KB smem + 256 TMEM columns per CTA -> two CTAs per SM overlap each other's MMA and MUFU phases.
 #include "common.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace tld {
@@ -47,6 +48,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
   const int row_k = b * n_tok;                // first key row of this sample
   const int col_q = head * TA_HD, col_k = D + head * TA_HD, col_v = 2 * D + head * TA_HD;
 
+  pdl_launch_dependents();
   if (warp == 4) {
     if (elect_one()) {
       tma_prefetch_desc(&tmap_qkv);
@@ -58,6 +60,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       mbar_init(bar_p, 128);
       mbar_init(bar_o, 1);
       fence_mbar_init();
+      pdl_wait();  // qkv is the previous kernel's output
       // first loads go out before the TMEM allocation / CTA-wide sync
       mbar_expect_tx(bar_q, TA_Q_BYTES);
       tma_load_2d(sQ, &tmap_qkv, bar_q, col_q, row_q);
@@ -73,6 +76,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // every thread (the epilogue updates x, which earlier kernels read)
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;         // S: columns [0,128)
   const uint32_t tmem_o = tmem_base + 128;   // O chunk: columns [128,192)
@@ -238,9 +242,7 @@ int launch_self_attention_tc(const bf16* qkv, float* x, int B, int n_tok, int D,
   if (make_tmap_2d(&tq, qkv, false, T, 3LL * D, 3LL * D, 128)) return 1;
   if (make_tmap_2d(&tx, x, true, T, D, D, 32)) return 1;
   dim3 grid(n_tok / TA_BQ, D / 64, B);
-  attention_tc_kernel<<<grid, TA_THREADS, TA_SMEM, st>>>(tq, tx, n_tok, D);
-  TLD_CUDA_OK(cudaGetLastError());
-  return 0;
+  return launch_pdl(attention_tc_kernel, grid, dim3(TA_THREADS), TA_SMEM, st, tq, tx, n_tok, D);
 }
 
 }  // namespace tld

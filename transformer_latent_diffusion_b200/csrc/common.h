@@ -27,6 +27,7 @@ const char* last_error();
   } while (0)
 
 int sm_count();
+void set_pdl(int v);  // 1 = launch the step kernels with programmatic dependent launch, 0 = plain launches (default)
 
 // ---------------------------------------------------------------- gemm.cu
 struct XattnArgs {

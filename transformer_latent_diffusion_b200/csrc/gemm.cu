@@ -5,6 +5,7 @@
 
 #include "common.h"
 #include "gemm_tcgen05.cuh"
+#include "launch.h"
 
 namespace tld {
 
@@ -79,13 +80,15 @@ static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensor
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTAS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   TLD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, M, N, K, ep));
   return 0;
 }

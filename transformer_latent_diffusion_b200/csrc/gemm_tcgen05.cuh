@@ -122,6 +122,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int first_tile = blockIdx.x / CTAS;      // both CTAs of a pair walk the same tile sequence
   const int tile_step = gridDim.x / CTAS;
 
+  pdl_launch_dependents();
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -150,6 +151,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tc_fence_before();
   if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
+  pdl_wait();  // prologue above overlaps the previous kernel's tail; operands / outputs are touched only from here on
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {

@@ -22,6 +22,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// launch_dependents: the next kernel in the stream/graph may start being scheduled once every CTA of this grid has
+// executed this (or exited); wait: block until all prerequisite grids have COMPLETED and their writes are visible.
+// Both are no-ops when the kernel was launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

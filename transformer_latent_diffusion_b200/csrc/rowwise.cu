@@ -4,6 +4,7 @@
 #include <math.h>
 
 #include "common.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace tld {
@@ -30,9 +31,11 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __rest
                                                              const float* __restrict__ beta, bf16* __restrict__ y,
                                                              int rows) {
   constexpr int D = V * 128;
+  pdl_launch_dependents();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
+  pdl_wait();
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
   float4 v[V];
   float s = 0.f;
@@ -69,7 +72,7 @@ int launch_layernorm_bf16(const float* x, const float* gamma, const float* beta,
   const int grid = (rows + 7) / 8;
   switch (D / 128) {
 #define LN_CASE(V) \
-  case V: layernorm_bf16_kernel<V><<<grid, 256, 0, st>>>(x, gamma, beta, y, rows); break;
+  case V: if (launch_pdl(layernorm_bf16_kernel<V>, dim3(grid), dim3(256), 0, st, x, gamma, beta, y, rows)) return 1; break;
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
 #undef LN_CASE
   }
@@ -90,7 +93,9 @@ __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ x,
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = img / patch, N = g * g, pd = C * patch * patch;
   const long long tok = (long long)blockIdx.x * 8 + wib;
+  pdl_launch_dependents();
   if (tok >= (long long)Bout * N) return;
+  pdl_wait();
   const int b = int(tok / N), n = int(tok % N);
   const int gy = n / g, gx = n % g;
   const float* xb = x + (size_t)(b % Bx) * C * img * img;
@@ -186,7 +191,7 @@ int launch_embed(const float* x, int Bx, int Bout, int C, int img, int patch, in
   const int grid = int((toks + 7) / 8);
   switch (D / 128) {
 #define EM_CASE(V) \
-  case V: embed_kernel<V><<<grid, 256, 0, st>>>(x, Bx, Bout, C, img, patch, w, out, sv); break;
+  case V: if (launch_pdl(embed_kernel<V>, dim3(grid), dim3(256), 0, st, x, Bx, Bout, C, img, patch, w, out, sv)) return 1; break;
     EM_CASE(1) EM_CASE(2) EM_CASE(3) EM_CASE(4) EM_CASE(5) EM_CASE(6) EM_CASE(7) EM_CASE(8)
 #undef EM_CASE
   }
@@ -520,9 +525,11 @@ __global__ void __launch_bounds__(256) dwconv_gelu_g16_kernel(const __grid_const
   uint64_t* bar = reinterpret_cast<uint64_t*>(tile + G * G * 128);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = blockIdx.x * 64, b = blockIdx.y;
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
+    pdl_wait();  // h is the previous kernel's output
     mbar_expect_tx(bar, G * G * 128);
     tma_load_2d(tile, &tmap_h, bar, c0, b * G * G);
   }
@@ -533,6 +540,7 @@ __global__ void __launch_bounds__(256) dwconv_gelu_g16_kernel(const __grid_const
   for (int tp = 0; tp < 9; ++tp) w[tp] = __ldg(reinterpret_cast<const float2*>(w9 + (size_t)tp * C + ch));
   const float2 bs = __ldg(reinterpret_cast<const float2*>(bias + ch));
   __syncthreads();  // barrier init visible before anyone polls it
+  pdl_wait();       // every thread: the output buffer may still be read by an earlier kernel
   mbar_wait(bar, 0);
 
   const int y0 = 2 * warp;  // output rows y0, y0+1; input rows y0-1 .. y0+2
@@ -591,9 +599,7 @@ int launch_dwconv_gelu(const bf16* h, const float* w9, const float* bias, bf16* 
     constexpr int smem = 1024 + 16 * 16 * 128 + 64;
     CUtensorMap th;
     if (make_tmap_2d(&th, h, false, (long long)B * 256, C, C, 256)) return 1;
-    dwconv_gelu_g16_kernel<<<dim3(C / 64, B), 256, smem, st>>>(th, w9, bias, g, C);
-    TLD_CUDA_OK(cudaGetLastError());
-    return 0;
+    return launch_pdl(dwconv_gelu_g16_kernel, dim3(C / 64, B), dim3(256), smem, st, th, w9, bias, g, C);
   }
   switch (grid) {
     case 8: dwconv_gelu_grid_kernel<8><<<blocks, 256, 0, st>>>(h, w9, bias, g, B, C); break;
@@ -634,10 +640,71 @@ __global__ void __launch_bounds__(256) outproj_kernel(const float* __restrict__ 
   }
 }
 
+// Fast path for patch_dim 16 (4 channels x 2x2): the [16, D] weight lives in shared memory, a warp keeps the token row in
+// registers and loops over tokens (persistent grid); lane o keeps output o.
+template <int V>
+__global__ void __launch_bounds__(256) outproj16_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ out,
+                                                        long long T, int C, int img, int patch) {
+  constexpr int D = V * 128;
+  extern __shared__ __align__(16) float s_w[];  // [16][D]
+  pdl_launch_dependents();
+  for (int i = threadIdx.x; i < 16 * D / 4; i += 256) reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
+  __syncthreads();
+  pdl_wait();
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = img / patch, N = g * g;
+  for (long long tok = (long long)blockIdx.x * 8 + wib; tok < T; tok += (long long)gridDim.x * 8) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)tok * D);
+    float4 xv[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) xv[j] = xr[lane + 32 * j];
+    float mine = 0.f;  // lane o ends up with output o
+#pragma unroll 1
+    for (int o = 0; o < 16; ++o) {
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float4 wv = reinterpret_cast<const float4*>(s_w + o * D)[lane + 32 * j];
+        a += xv[j].x * wv.x + xv[j].y * wv.y + xv[j].z * wv.z + xv[j].w * wv.w;
+      }
+      a = warp_sum(a);
+      if (lane == o) mine = a;
+    }
+    const float tot = mine;
+    const int o = lane;
+    if (lane < 16) {
+      const int b = int(tok / N), n = int(tok % N), gy = n / g, gx = n % g;
+      const int c = o / (patch * patch), p1 = (o / patch) % patch, p2 = o % patch;
+      out[((size_t)b * C + c) * img * img + (size_t)(gy * patch + p1) * img + gx * patch + p2] = tot + bias[o];
+    }
+  }
+}
+
 int launch_outproj(const float* x, const float* w, const float* b, float* out, int B, int C, int img, int patch,
                    int D, cudaStream_t st) {
   TLD_CHECK(D % 4 == 0, "outproj: embed_dim must be a multiple of 4");
   const long long toks = (long long)B * (img / patch) * (img / patch);
+  if (C * patch * patch == 16 && D % 128 == 0 && D <= 768) {
+    const int smem = 16 * D * 4;
+    long long nb = (toks + 7) / 8;
+    if (nb > 4LL * sm_count()) nb = 4LL * sm_count();
+    switch (D / 128) {
+#define OP_CASE(V)                                                                                               \
+  case V: {                                                                                                      \
+    static bool set = false;                                                                                     \
+    if (!set) {                                                                                                  \
+      TLD_CUDA_OK(cudaFuncSetAttribute(outproj16_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152)); \
+      set = true;                                                                                                \
+    }                                                                                                            \
+    if (launch_pdl(outproj16_kernel<V>, dim3((int)nb), dim3(256), smem, st, x, w, b, out, toks, C, img, patch)) return 1; \
+  } break;
+      OP_CASE(1) OP_CASE(2) OP_CASE(3) OP_CASE(4) OP_CASE(5) OP_CASE(6)
+#undef OP_CASE
+    }
+    TLD_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   outproj_kernel<<<int((toks + 7) / 8), 256, 0, st>>>(x, w, b, out, B, C, img, patch, D);
   TLD_CUDA_OK(cudaGetLastError());
   return 0;
@@ -651,6 +718,8 @@ __global__ void __launch_bounds__(256) cfg_update_kernel(const float* __restrict
                                                          float* __restrict__ x0_prev, float* __restrict__ x0_out,
                                                          const StepCoef* __restrict__ table,
                                                          const int* __restrict__ step_ptr, int B, int C, int hw) {
+  pdl_launch_dependents();
+  pdl_wait();
   const StepCoef sc = table[*step_ptr];
   const long long n = (long long)B * C * hw;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -672,19 +741,20 @@ __global__ void __launch_bounds__(256) cfg_update_kernel(const float* __restrict
   x0_prev[i] = x0;
 }
 
-__global__ void advance_step_kernel(int* step_ptr) { *step_ptr += 1; }
+__global__ void advance_step_kernel(int* step_ptr) {
+  pdl_launch_dependents();
+  pdl_wait();
+  *step_ptr += 1;
+}
 
 int launch_cfg_update(const float* model_out, float* x_t, float* x0_prev, float* x0_out, const StepCoef* table,
                       const int* step_ptr, int B, int C, int hw, cudaStream_t st) {
   const long long n = (long long)B * C * hw;
-  cfg_update_kernel<<<int((n + 255) / 256), 256, 0, st>>>(model_out, x_t, x0_prev, x0_out, table, step_ptr, B, C, hw);
-  TLD_CUDA_OK(cudaGetLastError());
-  return 0;
+  return launch_pdl(cfg_update_kernel, dim3(int((n + 255) / 256)), dim3(256), 0, st, model_out, x_t, x0_prev, x0_out, table, step_ptr,
+                    B, C, hw);
 }
 int launch_advance_step(int* step_ptr, cudaStream_t st) {
-  advance_step_kernel<<<1, 1, 0, st>>>(step_ptr);
-  TLD_CUDA_OK(cudaGetLastError());
-  return 0;
+  return launch_pdl(advance_step_kernel, dim3(1), dim3(1), 0, st, step_ptr);
 }
 
 }  // namespace tld
