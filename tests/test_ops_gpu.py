@@ -130,10 +130,11 @@ def test_layernorm(lib, rows, D):
     assert rel_fro(y.float(), ref) < 3e-3
 
 
-@pytest.mark.parametrize("impl", [1, 2])
-@pytest.mark.parametrize("B,n_tok,D", [(1, 64, 128), (2, 256, 128), (3, 256, 768), (1, 1024, 256), (1, 4096, 128)])
+@pytest.mark.parametrize("impl", [1, 2, 3])
+@pytest.mark.parametrize("B,n_tok,D", [(1, 64, 128), (2, 256, 128), (3, 256, 768), (1, 1024, 256), (1, 4096, 128),
+                                       (40, 128, 768), (17, 256, 768), (2, 1024, 768)])   # > 2 tiles per persistent CTA
 def test_self_attention(lib, B, n_tok, D, impl):
-    if impl == 2 and n_tok % 128:
+    if impl >= 2 and n_tok % 128:
         pytest.skip("tcgen05 attention needs n_tok % 128 == 0")
     g = torch.Generator(device="cuda").manual_seed(5)
     T = B * n_tok
@@ -147,6 +148,31 @@ def test_self_attention(lib, B, n_tok, D, impl):
     lib.check(lib.load().tld_op_self_attention(lib.ptr(qkv), lib.ptr(x), B, n_tok, D, impl, _stream()), "attn")
     # P is rounded to bf16 before the PV product (as in every flash kernel): error ~2^-9 relative on o
     assert rel_fro(x - (ref - o), o) < 6e-3, _err_map(x, ref)
+
+
+@pytest.mark.parametrize("emu", [0, 4, 6, 8, 10])
+@pytest.mark.parametrize("qk_scale", [1.0, 4.0])
+def test_self_attention_persistent_variants(lib, emu, qk_scale):
+    """attention_tc2: every FMA-pipe exp2 share, and (qk_scale 4: score std ~23 in the exp2 domain) the lazy-rescale path
+    where the row maximum keeps jumping by more than 2^8 between 64-key chunks."""
+    B, n_tok, D = 5, 512, 256
+    g = torch.Generator(device="cuda").manual_seed(50 + emu)
+    T = B * n_tok
+    qkv = torch.randn(T, 3 * D, device="cuda", generator=g)
+    qkv[:, : 2 * D] *= qk_scale
+    qkv = qkv.bfloat16()
+    x = torch.zeros(T, D, device="cuda")
+    H = D // 64
+    q, k, v = (t.float().view(B, n_tok, H, 64).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=1))
+    ref = (torch.softmax((q @ k.transpose(-1, -2)) / 8.0, -1) @ v).permute(0, 2, 1, 3).reshape(T, D)
+    L = lib.load()
+    lib.check(L.tld_set_option(b"attention_exp_emu", emu), "opt")
+    try:
+        lib.check(L.tld_op_self_attention(lib.ptr(qkv), lib.ptr(x), B, n_tok, D, 3, _stream()), "attn")
+        torch.cuda.synchronize()
+    finally:
+        lib.check(L.tld_set_option(b"attention_exp_emu", 6), "opt")
+    assert rel_fro(x, ref) < 6e-3, _err_map(x, ref)
 
 
 @pytest.mark.parametrize("B,grid,C", [(1, 8, 512), (2, 16, 1024), (2, 16, 3072), (1, 32, 512)])

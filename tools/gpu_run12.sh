@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out && rm -f gpurun_out/summary.txt
+run() { name=$1; shift; timeout -k 10 "$@" > gpurun_out/$name.log 2>&1; echo "$name exit=$?" >> gpurun_out/summary.txt; tail -3 gpurun_out/$name.log >> gpurun_out/summary.txt; }
+run t_attn 300 python -m pytest tests/test_ops_gpu.py -q -k attention --no-header -p no:cacheprovider
+run t_fwd 600 python -m pytest tests/test_forward_gpu.py tests/test_train_gpu.py -q --no-header -p no:cacheprovider
+for impl in 2 3; do
+run time256_$impl 300 python tools/time_forward.py --batch 64 --reps 3 --forward-only --attn-impl $impl
+run time512_$impl 300 python tools/time_forward.py --img 64 --batch 16 --reps 3 --forward-only --attn-impl $impl
+run time1024_$impl 300 python tools/time_forward.py --img 128 --batch 4 --reps 3 --forward-only --attn-impl $impl
+done
+timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_fwd.csv \
+  python tools/time_forward.py --batch 64 --reps 1 --forward-only > gpurun_out/ncu_fwd.log 2>&1
+timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_1024.csv \
+  python tools/time_forward.py --img 128 --batch 4 --reps 1 --forward-only > gpurun_out/ncu_1024.log 2>&1
+cat gpurun_out/summary.txt

@@ -247,8 +247,14 @@ int tld_set_option(const char* key, int value) {
     return 0;
   }
   if (k == "attention_impl") {
-    TLD_CHECK(value >= 0 && value <= 2, "attention_impl must be 0, 1 or 2");
+    TLD_CHECK(value >= 0 && value <= 3, "attention_impl must be 0, 1, 2 or 3");
     g_attention_impl = value;
+    return 0;
+  }
+  if (k == "attention_exp_emu") {
+    TLD_CHECK(value == 0 || value == 4 || value == 6 || value == 8 || value == 10,
+              "attention_exp_emu (exp2 pairs per 16 evaluated on the FMA pipe) must be 0, 4, 6, 8 or 10");
+    set_attention_exp_emu(value);
     return 0;
   }
   return fail("tld_set_option: unknown key " + k);
@@ -524,7 +530,8 @@ int tld_op_layernorm(const float* x, const float* gamma, const float* beta, uint
 }
 
 int tld_op_self_attention(const uint16_t* qkv, float* x, int batch, int n_tok, int D, int impl, void* stream) {
-  TLD_CHECK(impl >= 0 && impl <= 2, "tld_op_self_attention: impl must be 0 (auto), 1 (mma.sync) or 2 (tcgen05)");
+  TLD_CHECK(impl >= 0 && impl <= 3,
+            "tld_op_self_attention: impl must be 0 (auto), 1 (mma.sync), 2 (tcgen05 tile-per-CTA) or 3 (tcgen05 persistent)");
   return launch_self_attention(reinterpret_cast<const bf16*>(qkv), x, batch, n_tok, D,
                                reinterpret_cast<cudaStream_t>(stream), impl);
 }

@@ -122,5 +122,7 @@ int make_tmap_2d(CUtensorMap* m, const void* base, bool is_f32, long long rows, 
 int launch_self_attention(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st, int impl = 0);
 int launch_self_attention_mma(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st);
 int launch_self_attention_tc(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st);
+int launch_self_attention_tc2(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st);
+void set_attention_exp_emu(int pairs_of_16);  // attention_tc2: share of exp2 evaluated on the FMA pipe instead of MUFU
 
 }  // namespace tld

@@ -286,6 +286,31 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+// explicit shared-window accesses (pointers derived from the 1024-aligned dynamic-smem base otherwise compile to generic LD/ST)
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -312,6 +337,31 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
       : "=l"(d)
       : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
   return *reinterpret_cast<float2*>(&d);
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {  // FMNMX3 (sm_100)
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// 2^x for x <= 0 on the FMA/ALU pipes instead of MUFU (16 results/clk/SM on B200): Cody-Waite split x = n + f with the
+// 1.5*2^23 rounding trick, 2^f for f in [-0.5, 0.5] by a degree-3 minimax polynomial (relative error 7.5e-5, far below the
+// bf16 rounding of P), exponent added with one integer shift-add.  Inputs are clamped at -125 (result ~2^-125 ~ 0).
+__device__ __forceinline__ float2 exp2_fma2(float2 x) {
+  const float magic = 12582912.f;
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 xr = fadd2(x, make_float2(magic, magic));                                  // low mantissa bits = n
+  const float2 nn = ffma2(xr, make_float2(-1.f, -1.f), make_float2(magic, magic));        // -n (exact)
+  const float2 f = fadd2(x, nn);
+  float2 p = ffma2(f, make_float2(0.05517027899622917f, 0.05517027899622917f),
+                   make_float2(0.2426076978445053f, 0.2426076978445053f));
+  p = ffma2(p, f, make_float2(0.693260908126831f, 0.693260908126831f));
+  p = ffma2(p, f, make_float2(0.9999282956123352f, 0.9999282956123352f));
+  p.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(xr.x) << 23));
+  p.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(xr.y) << 23));
+  return p;
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {  // MUFU.EX2; -inf -> 0
