@@ -17,14 +17,29 @@
 #include "launch.h"
 #include "ptx.cuh"
 
+#ifdef TLD_TRACE
+// developer instrumentation (never compiled into the shipped library): per-role clock64 stamps of CTA 0
+__device__ unsigned long long g_t2_trace[3][2048];
+#define T2_TR(role, id)                                                                         \
+  do {                                                                                          \
+    if (blockIdx.x == 0 && trn < 2048) g_t2_trace[role][trn++] = (clock64() << 8) | (id);       \
+  } while (0)
+extern "C" __attribute__((visibility("default"))) int tld_debug_attention_trace(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_t2_trace, sizeof(g_t2_trace));
+}
+#else
+#define T2_TR(role, id) \
+  do {                  \
+  } while (0)
+#endif
+
 namespace tld {
 
 constexpr int T2_BQ = 128, T2_BK = 64, T2_HD = 64, T2_THREADS = 320;
 constexpr int T2_Q_BYTES = T2_BQ * T2_HD * 2;     // 16 KB
 constexpr int T2_KV_BYTES = T2_BK * T2_HD * 2;    // 8 KB each for K and V
-constexpr int T2_P_BYTES = T2_BQ * T2_BK * 2;     // 16 KB
 constexpr int T2_STG_BYTES = 8 * 32 * 128;        // 32 KB: one [32 x 128 B] slab per softmax warp
-constexpr int T2_SMEM = 1024 + T2_Q_BYTES + 2 * 2 * T2_KV_BYTES + T2_P_BYTES + T2_STG_BYTES + 256 + 4096;
+constexpr int T2_SMEM = 1024 + 2 * T2_Q_BYTES + 2 * 2 * T2_KV_BYTES + T2_STG_BYTES + 256 + 4096;
 
 template <int EMU>
 __global__ void __launch_bounds__(T2_THREADS, 2)
@@ -32,22 +47,24 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                      const __grid_constant__ CUtensorMap tmap_x, int n_tok, int D, int B) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + T2_Q_BYTES;                       // slot s: K at sKV + s*16K, V at +8K
-  uint8_t* sP = sKV + 2 * 2 * T2_KV_BYTES;
-  uint8_t* sStg = sP + T2_P_BYTES;
+  uint8_t* sQ = smem;                                   // [2] double-buffered across tiles
+  uint8_t* sKV = sQ + 2 * T2_Q_BYTES;                   // slot s: K at sKV + s*16K, V at +8K
+  uint8_t* sStg = sKV + 2 * 2 * T2_KV_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + T2_STG_BYTES);
-  uint64_t* q_full = bars + 0;
-  uint64_t* q_empty = bars + 1;
+  uint64_t* q_full = bars + 0;    // [2]
+  uint64_t* q_empty = bars + 14;  // [2]
   uint64_t* k_full = bars + 2;    // [2]  K and V slots are released separately: K(c) right after S(c) retires, V(c) after
   uint64_t* k_empty = bars + 4;   // [2]  PV(c) - so the K load runs a full softmax period ahead of its S-MMA
   uint64_t* v_full = bars + 6;    // [2]
   uint64_t* v_empty = bars + 8;   // [2]
   uint64_t* s_full = bars + 10;
   uint64_t* s_free = bars + 11;   // 256 arrivals: S(c) is in registers
-  uint64_t* p_full = bars + 12;   // 256 arrivals: P(c) written
-  uint64_t* o_full = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* p_full = bars + 12;   // [2] 256 arrivals: P(c) written into P buffer c & 1.  One barrier per buffer: the softmax
+                                  // threads may run a whole chunk ahead of the MMA thread (they do not depend on V), and a
+                                  // single barrier could then complete two phases between two polls of the MMA thread
+  uint64_t* o_full = bars + 16;   // [2] PV(c) retired, one barrier per chunk parity: the softmax threads do not wait on every
+                                  // phase, and a lone barrier would alias when a thread is two chunks behind
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   float* s_xchg_all = reinterpret_cast<float*>(bars + 32);  // [2 tile parities][m|l][2 halves][128]: alternating buffers
                                                             // make tile k+2's write safe behind tile k+1's barrier
 
@@ -61,9 +78,9 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tma_prefetch_desc(&tmap_q);
       tma_prefetch_desc(&tmap_kv);
       tma_prefetch_desc(&tmap_x);
-      mbar_init(q_full, 1);
-      mbar_init(q_empty, 1);
       for (int s = 0; s < 2; ++s) {
+        mbar_init(&q_full[s], 1);
+        mbar_init(&q_empty[s], 1);
         mbar_init(&k_full[s], 1);
         mbar_init(&k_empty[s], 1);
         mbar_init(&v_full[s], 1);
@@ -71,8 +88,10 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
       mbar_init(s_full, 1);
       mbar_init(s_free, 256);
-      mbar_init(p_full, 256);
-      mbar_init(o_full, 1);
+      mbar_init(&p_full[0], 256);
+      mbar_init(&p_full[1], 256);
+      mbar_init(&o_full[0], 1);
+      mbar_init(&o_full[1], 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -84,8 +103,9 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   tc_fence_after();
   pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;        // columns [0,64)
-  const uint32_t tmem_o = tmem_base + 64;   // O_0 columns [64,128), O_1 columns [128,192)
+  const uint32_t tmem_s = tmem_base;        // S: columns [0,64) fp32
+  const uint32_t tmem_p = tmem_base + 64;   // P: two buffers of 32 columns (64 keys as packed bf16 pairs), [64,96) and [96,128)
+  const uint32_t tmem_o = tmem_base + 128;  // O_0 columns [128,192), O_1 columns [192,256)
 
   auto tile_coords = [&](int tile, int& row_q, int& row_k, int& head) {
     const int qt = tile % q_tiles, bh = tile / q_tiles;
@@ -100,6 +120,17 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     if (elect_one()) {
       int it = 0;       // tile counter of this CTA
       int ck = 0;       // global chunk counter (ring position)
+      [[maybe_unused]] int trn = 0;
+      auto load_q = [&](int tile, int n) {   // n = tile counter of this CTA; Q slot n & 1
+        int row_q, row_k, head;
+        tile_coords(tile, row_q, row_k, head);
+        const int slot = n & 1;
+        mbar_wait(&q_empty[slot], ((n >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[slot], T2_Q_BYTES);
+        T2_TR(0, 0);
+        tma_load_2d(sQ + slot * T2_Q_BYTES, &tmap_q, &q_full[slot], head * T2_HD, row_q);
+      };
+      load_q(blockIdx.x, 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         int row_q, row_k, head;
         tile_coords(tile, row_q, row_k, head);
@@ -107,17 +138,28 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           const int slot = g & 1;
           mbar_wait(&k_empty[slot], ((g >> 1) & 1) ^ 1);
           mbar_expect_tx(&k_full[slot], T2_KV_BYTES);
+          T2_TR(0, 1);
           tma_load_2d(sKV + slot * 2 * T2_KV_BYTES, &tmap_kv, &k_full[slot], D + head * T2_HD, row_k + c * T2_BK);
         };
-        load_k(0, ck);                       // its slot frees up before Q does (Q waits for the previous tile's last S)
-        mbar_wait(q_empty, (it & 1) ^ 1);
-        mbar_expect_tx(q_full, T2_Q_BYTES);
-        tma_load_2d(sQ, &tmap_q, q_full, head * T2_HD, row_q);
+        load_k(0, ck);
+        if (tile + (int)gridDim.x < num_tiles) {
+          // next tile of this CTA: its Q goes into the other Q buffer a whole tile ahead, and its first K/V boxes are pulled
+          // into L2 so that their TMA loads at the tile boundary take an L2 hit instead of a DRAM round trip
+          load_q(tile + gridDim.x, it + 1);
+          int nq, nk, nh;
+          tile_coords(tile + gridDim.x, nq, nk, nh);
+          const int npf = n_chunks < 4 ? n_chunks : 4;
+          for (int c = 0; c < npf; ++c) {
+            tma_prefetch_2d(&tmap_kv, D + nh * T2_HD, nk + c * T2_BK);
+            tma_prefetch_2d(&tmap_kv, 2 * D + nh * T2_HD, nk + c * T2_BK);
+          }
+        }
         for (int c = 0; c < n_chunks; ++c, ++ck) {   // K runs one chunk ahead of V
           if (c + 1 < n_chunks) load_k(c + 1, ck + 1);
           const int slot = ck & 1;
           mbar_wait(&v_empty[slot], ((ck >> 1) & 1) ^ 1);
           mbar_expect_tx(&v_full[slot], T2_KV_BYTES);
+          T2_TR(0, 2);
           tma_load_2d(sKV + slot * 2 * T2_KV_BYTES + T2_KV_BYTES, &tmap_kv, &v_full[slot], 2 * D + head * T2_HD,
                       row_k + c * T2_BK);
         }
@@ -128,48 +170,54 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(T2_BQ, T2_BK, 0, 0);   // S = Q K^T : both K-major
       constexpr uint32_t idesc_o = umma_idesc_bf16(T2_BQ, T2_HD, 0, 1);   // O = P V   : V MN-major
-      const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
-      const uint64_t pdesc = umma_smem_desc_sw128(smem_u32(sP), 16, 1024);
-      int it = 0, ck = 0;
-      uint32_t gs = 0;  // global count of S MMAs issued (phase of s_full / s_free / p_full / o_full)
-      auto issue_s = [&](int slot) {
+      const uint64_t qdesc0 = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+      [[maybe_unused]] int trn = 0;
+      auto issue_s = [&](int slot, int qslot) {
+        T2_TR(1, 1);
         const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sKV + slot * 2 * T2_KV_BYTES), 16, 1024);
+        const uint64_t qdesc = qdesc0 + uint64_t(qslot * (T2_Q_BYTES >> 4));
 #pragma unroll
         for (int k = 0; k < T2_HD / 16; ++k) umma_ss_f16(tmem_s, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
         umma_commit(s_full);
         umma_commit(&k_empty[slot]);
       };
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        mbar_wait(q_full, it & 1);
-        // first S of the tile: needs the K slot and the previous S pulled out of TMEM by the softmax threads
-        mbar_wait(&k_full[ck & 1], (ck >> 1) & 1);
-        if (gs > 0) mbar_wait(s_free, (gs - 1) & 1);
-        tc_fence_after();
-        issue_s(ck & 1);
-        ++gs;
-        for (int c = 0; c < n_chunks; ++c, ++ck) {
-          const int slot = ck & 1;
-          const uint32_t cur = gs - 1;  // index of S(c) in the global sequence
-          if (c + 1 < n_chunks) {       // S(c+1) overlaps softmax(c)
-            mbar_wait(&k_full[(ck + 1) & 1], ((ck + 1) >> 1) & 1);
-            mbar_wait(s_free, cur & 1);
-            tc_fence_after();
-            issue_s((ck + 1) & 1);
-            ++gs;
-          } else {
-            umma_commit(q_empty);       // every S-MMA of this tile has been issued: Q is free once they retire
-          }
-          mbar_wait(&v_full[slot], (ck >> 1) & 1);
-          mbar_wait(p_full, cur & 1);
+      // One flat sequence of chunks g = 0 .. G-1 over all tiles of this CTA: S(g+1) is always issued before the wait for
+      // P(g), also across a tile boundary (the next tile's first S overlaps the last softmax of the current tile).
+      const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int G = my_tiles * n_chunks;
+      int c = 0, it = 0;  // chunk within the tile, tile counter of S(g)
+      mbar_wait(&q_full[0], 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      for (int g = 0; g < G; ++g) {
+        if (g + 1 < G) {
+          const int c1 = (c + 1 == n_chunks) ? 0 : c + 1;
+          const int it1 = it + (c1 == 0);   // tile counter of S(g+1)
+          if (c1 == 0) mbar_wait(&q_full[it1 & 1], (it1 >> 1) & 1);
+          mbar_wait(&k_full[(g + 1) & 1], ((g + 1) >> 1) & 1);
+          mbar_wait(s_free, g & 1);   // S(g) is in the softmax threads' registers
           tc_fence_after();
-          const uint32_t vbase = smem_u32(sKV + slot * 2 * T2_KV_BYTES + T2_KV_BYTES);
+          issue_s((g + 1) & 1, it1 & 1);
+          if (c1 == n_chunks - 1) umma_commit(&q_empty[it1 & 1]);   // the tile's last S-MMA is queued
+        }
+        const int slot = g & 1;
+        mbar_wait(&v_full[slot], (g >> 1) & 1);
+        mbar_wait(&p_full[slot], (g >> 1) & 1);
+        tc_fence_after();
+        T2_TR(1, 2);
+        const uint32_t vbase = smem_u32(sKV + slot * 2 * T2_KV_BYTES + T2_KV_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < T2_BK / 16; ++kk) {   // keys [16 kk, +16) belong to half kk >> 1 -> accumulator O_(kk>>1)
-            const uint64_t bdesc = umma_smem_desc_sw128(vbase + kk * 16 * 128, T2_BK * 128, 1024);
-            umma_ss_f16(tmem_o + (kk >> 1) * 64, pdesc + 2 * kk, bdesc, idesc_o, (c | (kk & 1)) != 0);
-          }
-          umma_commit(o_full);
-          umma_commit(&v_empty[slot]);
+        for (int kk = 0; kk < T2_BK / 16; ++kk) {   // keys [16 kk, +16) belong to half kk >> 1 -> accumulator O_(kk>>1)
+          const uint64_t bdesc = umma_smem_desc_sw128(vbase + kk * 16 * 128, T2_BK * 128, 1024);
+          // A = P(g) straight from TMEM (buffer g & 1, 8 columns of packed bf16 pairs per K=16 step)
+          umma_ts_f16(tmem_o + (kk >> 1) * 64, tmem_p + slot * 32 + kk * 8, bdesc, idesc_o, (c | (kk & 1)) != 0);
+        }
+        umma_commit(&o_full[slot]);
+        umma_commit(&v_empty[slot]);
+        if (++c == n_chunks) {
+          c = 0;
+          ++it;
         }
       }
     }
@@ -186,16 +234,67 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
     const uint32_t tmem_mine = tmem_o + lane_base + hf * 64, tmem_other = tmem_o + lane_base + (hf ^ 1) * 64;
     const float sl2 = 0.125f * 1.4426950408889634f;
-    const uint32_t p_row = smem_u32(sP) + r * 128, xchg0 = smem_u32(s_xchg_all);
+    const uint32_t xchg0 = smem_u32(s_xchg_all);
     uint32_t gs = 0, it = 0;
+    [[maybe_unused]] int trn = threadIdx.x == 0 ? 0 : 4096;
+    // tile epilogue (merge the two key halves, x += O / l); runs AFTER the exp2 work of the next tile's first chunk so that
+    // the latency of the last P V product is hidden (O_0/O_1 stay intact until that chunk's p_full arrival)
+    auto epilogue = [&](float m_fin, float l_fin, int row_q, int head, uint32_t g_last, uint32_t xpar) {
+      const uint32_t xb = xchg0 + xpar * 2048;   // [2 tile parities][m|l][2 halves][128 rows]
+      sts_f32(xb + (hf * 128 + r) * 4, m_fin);
+      sts_f32(xb + 1024 + (hf * 128 + r) * 4, l_fin);
+      named_bar_sync(1, 256);
+      const float m_p = lds_f32(xb + ((hf ^ 1) * 128 + r) * 4), l_p = lds_f32(xb + 1024 + ((hf ^ 1) * 128 + r) * 4);
+      const float m_all = fmaxf(m_fin, m_p);
+      float a_me = exp2f((m_fin - m_all) * sl2), a_p = exp2f((m_p - m_all) * sl2);
+      const float inv = 1.f / (l_fin * a_me + l_p * a_p);
+      a_me *= inv;
+      a_p *= inv;
+      const uint32_t slab = smem_u32(sStg) + warp * (32 * 128);
+      if (lane == 0) bulk_wait_read<0>();  // the previous tile's reduce-add has finished reading this slab
+      __syncwarp();
+      mbar_wait(&o_full[g_last & 1], (g_last >> 1) & 1);   // the tile's last P V product has retired
+      tc_fence_after();
+      T2_TR(2, 3);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {   // output columns [32 hf + 16 j, +16) from both accumulators
+        uint32_t o0[16], o1[16];
+        tmem_ld_x16(tmem_mine + hf * 32 + j * 16, o0);
+        tmem_ld_x16(tmem_other + hf * 32 + j * 16, o1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            v[e] = __uint_as_float(o0[4 * q + e]) * a_me + __uint_as_float(o1[4 * q + e]) * a_p;
+          sts_v4(slab + lane * 128 + (((j * 4 + q) ^ (lane & 7)) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]),
+                 __float_as_uint(v[2]), __float_as_uint(v[3]));
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_2d(&tmap_x, reinterpret_cast<void*>(sStg + warp * (32 * 128)), head * T2_HD + hf * 32,
+                          row_q + (warp & 3) * 32);
+        bulk_commit();
+      }
+      T2_TR(2, 4);
+    };
+    bool pending = false;
+    float m_prev = 0.f, l_prev = 0.f;
+    int row_q_prev = 0, head_prev = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       int row_q, row_k, head;
       tile_coords(tile, row_q, row_k, head);
+      T2_TR(2, 0);
       float m_ref = -INFINITY, l_run = 0.f;
       for (int c = 0; c < n_chunks; ++c, ++gs) {
         const uint32_t ph = gs & 1;
         mbar_wait(s_full, ph);
         tc_fence_after();
+        T2_TR(2, 1);
         uint32_t s[32];
         tmem_ld_x32(tmem_s + lane_base + hf * 32, s);
         tmem_ld_wait();
@@ -217,7 +316,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
         l_run *= corr;
         if (fix_o) {  // rare: rescale this thread's O_hf in TMEM (no PV is in flight between o_full(c-1) and p_full(c))
-          mbar_wait(o_full, ph ^ 1);
+          mbar_wait(&o_full[(gs - 1) & 1], ((gs - 1) >> 1) & 1);
           tc_fence_after();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -244,54 +343,21 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           pk[i] = pack_bf16x2(p.x, p.y);
         }
         l_run += rs2.x + rs2.y;
-        if (c > 0 && !fix_o) mbar_wait(o_full, ph ^ 1);  // PV(c-1) has finished reading P(c-1)
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          sts_v4(p_row + (((hf * 4 + q) ^ (r & 7)) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        fence_proxy_async_smem();
-        mbar_arrive(p_full);
+        // S(c) retired => every earlier MMA retired, in particular PV(c-2), the last reader of P buffer c & 1
+        if (c == 0 && pending) epilogue(m_prev, l_prev, row_q_prev, head_prev, gs - 1, (it & 1) ^ 1);
+        tmem_st_x16(tmem_p + lane_base + (gs & 1) * 32 + hf * 16, pk);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[gs & 1]);
+        T2_TR(2, 2);
       }
-      // ---- tile epilogue: merge the two key halves, x += O / l
-      const uint32_t xb = xchg0 + (it & 1) * 2048;   // [2 tile parities][m|l][2 halves][128 rows]
-      sts_f32(xb + (hf * 128 + r) * 4, m_ref);
-      sts_f32(xb + 1024 + (hf * 128 + r) * 4, l_run);
-      named_bar_sync(1, 256);
-      const float m_p = lds_f32(xb + ((hf ^ 1) * 128 + r) * 4), l_p = lds_f32(xb + 1024 + ((hf ^ 1) * 128 + r) * 4);
-      const float m_all = fmaxf(m_ref, m_p);
-      float a_me = exp2f((m_ref - m_all) * sl2), a_p = exp2f((m_p - m_all) * sl2);
-      const float inv = 1.f / (l_run * a_me + l_p * a_p);
-      a_me *= inv;
-      a_p *= inv;
-      const uint32_t slab = smem_u32(sStg) + warp * (32 * 128);
-      if (lane == 0) bulk_wait_read<0>();  // the previous tile's reduce-add has finished reading this slab
-      __syncwarp();
-      mbar_wait(o_full, (gs - 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {   // output columns [32 hf + 16 j, +16) from both accumulators
-        uint32_t o0[16], o1[16];
-        tmem_ld_x16(tmem_mine + hf * 32 + j * 16, o0);
-        tmem_ld_x16(tmem_other + hf * 32 + j * 16, o1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float v[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            v[e] = __uint_as_float(o0[4 * q + e]) * a_me + __uint_as_float(o1[4 * q + e]) * a_p;
-          sts_v4(slab + lane * 128 + (((j * 4 + q) ^ (lane & 7)) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]),
-                 __float_as_uint(v[2]), __float_as_uint(v[3]));
-        }
-      }
-      tc_fence_before();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        tma_reduce_add_2d(&tmap_x, reinterpret_cast<void*>(sStg + warp * (32 * 128)), head * T2_HD + hf * 32,
-                          row_q + (warp & 3) * 32);
-        bulk_commit();
-      }
+      pending = true;
+      m_prev = m_ref;
+      l_prev = l_run;
+      row_q_prev = row_q;
+      head_prev = head;
     }
+    if (pending) epilogue(m_prev, l_prev, row_q_prev, head_prev, gs - 1, (it & 1) ^ 1);
     if (lane == 0) bulk_wait_read<0>();
   }
   tc_fence_before();
