@@ -169,6 +169,9 @@ int launch_gemm(int epi, const bf16* A, int lda, const bf16* W, int ldw, int M, 
   if (epi == EPI_XATTN_RESID_F32) {
     TLD_CHECK(xa != nullptr, "launch_gemm: cross-attention epilogue needs XattnArgs");
     TLD_CHECK(N % 64 == 0 && xa->n_tok % 64 == 0, "launch_gemm: cross-attention epilogue needs N and n_tok multiples of 64");
+    TLD_CHECK(xa->kv0_stride % 4 == 0 && xa->kv1_stride % 4 == 0 && xa->embed_dim % 4 == 0 &&
+                  (reinterpret_cast<uintptr_t>(xa->kv0) & 15) == 0 && (reinterpret_cast<uintptr_t>(xa->kv1) & 15) == 0,
+              "launch_gemm: cross-attention K/V rows must be 16-byte aligned (float4 staging)");
   }
   if (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_RESID_F32)
     TLD_CHECK(bias != nullptr && N % 64 == 0, "launch_gemm: bias epilogues need a bias and N % 64 == 0");

@@ -68,7 +68,7 @@ struct GemmSmem {
   static constexpr int B_BYTES = (BN / CTAS) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_BYTES = 4 * 2 * STG_SLAB;  // 4 warps x 2 buffers
-  static constexpr int KV_BYTES = (EPI == EPI_XATTN_RESID_F32) ? 2 * 4 * BN * 4 : 0;  // 2 samples x {k0,k1,v0,v1}
+  static constexpr int KV_BYTES = (EPI == EPI_XATTN_RESID_F32) ? 2 * 2 * 4 * BN * 4 : 0;  // 2 buffers x 2 samples x {k0,k1,v0,v1}
   static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - STG_BYTES - KV_BYTES - 256 /*barriers*/;
   static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
   static constexpr int TOTAL = 1024 + STAGES * STAGE_BYTES + STG_BYTES + KV_BYTES + 256;
@@ -77,11 +77,9 @@ struct GemmSmem {
 
 // write this lane's 128-byte row into a 128B-swizzled [32 x 128 B] slab (conflict-free per quarter-warp)
 __device__ __forceinline__ void stage_row(uint8_t* slab, int lane, const uint32_t (&v)[32]) {
+  const uint32_t row = smem_u32(slab) + lane * 128;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    uint4 q = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    *reinterpret_cast<uint4*>(slab + lane * 128 + ((j ^ (lane & 7)) << 4)) = q;
-  }
+  for (int j = 0; j < 8; ++j) sts_v4(row + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 
 template <int BN, int EPI, int CTAS>
@@ -262,6 +260,42 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       buf ^= 1;
     };
 
+    // cross-attention K/V staging (EPI_XATTN_RESID_F32 only): 2 samples x 4 vectors x BN columns as float4 pieces
+    constexpr int KV_LD = (2 * BN + 127) / 128;   // float4 loads per thread
+    float4 kv_pre[KV_LD];
+    const long long r0s = (EPI == EPI_XATTN_RESID_F32 && ep.step_ptr) ? (long long)(*ep.step_ptr) : -1;
+    auto kv_fetch = [&](int tile) {
+      const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * GEMM_BM;
+      const int n0 = (tile % n_tiles) * BN;
+      const int b_first = m0 / ep.n_tok;
+#pragma unroll
+      for (int u = 0; u < KV_LD; ++u) {
+        const int j = et + 128 * u;
+        const int s = j / BN, rem = j % BN;          // BN float4 per sample
+        const int vec = rem / (BN / 4), c = (rem % (BN / 4)) * 4;   // 0:k0 1:k1 2:v0 3:v1
+        const int b = b_first + s;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < 2 * BN && (long long)b * ep.n_tok < M && n0 + c < N) {
+          const long long r0 = r0s >= 0 ? r0s : (long long)b;
+          const float* src = (vec & 1) == 0 ? ep.kv0 + r0 * ep.kv0_stride : ep.kv1 + (long long)b * ep.kv1_stride;
+          val = __ldg(reinterpret_cast<const float4*>(src + (vec >= 2 ? ep.embed_dim : 0) + n0 + c));
+        }
+        kv_pre[u] = val;
+      }
+    };
+    auto kv_store = [&](uint32_t base) {
+#pragma unroll
+      for (int u = 0; u < KV_LD; ++u) {
+        const int j = et + 128 * u;
+        if (j < 2 * BN)
+          sts_v4(base + j * 16, __float_as_uint(kv_pre[u].x), __float_as_uint(kv_pre[u].y), __float_as_uint(kv_pre[u].z),
+                 __float_as_uint(kv_pre[u].w));
+      }
+    };
+    if constexpr (EPI == EPI_XATTN_RESID_F32) {
+      if (first_tile < num_tiles) kv_fetch(first_tile);
+    }
+
     int it = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
@@ -272,26 +306,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int slab_row = m0 + ew * 32;
 
       int sidx = 0;
+      uint32_t kvb = 0;
       if constexpr (EPI == EPI_XATTN_RESID_F32) {
-        // stage k0,k1,v0,v1 of the (at most two) samples this tile touches
-        const int b_first = m0 / ep.n_tok;
-        named_bar_sync(1, 128);  // previous tile's readers are done
-        const long long r0s = ep.step_ptr ? (long long)(*ep.step_ptr) : -1;
-        for (int i = et; i < 2 * 4 * BN; i += 128) {
-          const int c = i % BN;
-          const int vec = (i / BN) & 3;       // 0:k0 1:k1 2:v0 3:v1
-          const int s = i / (4 * BN);
-          const int b = b_first + s;
-          float val = 0.f;
-          if ((long long)b * ep.n_tok < M && n0 + c < N) {
-            const long long r0 = r0s >= 0 ? r0s : (long long)b;
-            const float* src = (vec & 1) == 0 ? ep.kv0 + r0 * ep.kv0_stride : ep.kv1 + (long long)b * ep.kv1_stride;
-            val = __ldg(src + (vec >= 2 ? ep.embed_dim : 0) + n0 + c);
-          }
-          smem_kv[i] = val;
-        }
+        // k0,k1,v0,v1 of the (at most two) samples this tile touches: fetched into registers one tile ahead (the global
+        // loads are in flight during the previous tile's epilogue math), parked in smem buffer it & 1.  One barrier per
+        // tile suffices: whoever writes buffer it & 1 has passed barrier it-1, which every reader of tile it-2 reached
+        // only after its reads.
+        kvb = smem_u32(smem_kv) + (it & 1) * (2 * 4 * BN * 4);
+        kv_store(kvb);
         named_bar_sync(1, 128);
-        sidx = row < M ? (row / ep.n_tok - b_first) : 0;
+        if (tile + tile_step < num_tiles) kv_fetch(tile + tile_step);
+        sidx = row < M ? (row / ep.n_tok - m0 / ep.n_tok) : 0;
+        kvb += sidx * 4 * BN * 4;
       }
 
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -299,21 +325,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + acc * BN;
 
       if constexpr (EPI == EPI_XATTN_RESID_F32) {
-        const float* kvb = smem_kv + sidx * 4 * BN;
 #pragma unroll 1
         for (int hc = 0; hc < BN / 64; ++hc) {
           uint32_t qa[32], qb[32];
           tmem_ld_x32(taddr + hc * 64, qa);
           tmem_ld_x32(taddr + hc * 64 + 32, qb);
           tmem_ld_wait();
-          const float4* k0 = reinterpret_cast<const float4*>(kvb + 0 * BN + hc * 64);
-          const float4* k1 = reinterpret_cast<const float4*>(kvb + 1 * BN + hc * 64);
-          const float4* v0 = reinterpret_cast<const float4*>(kvb + 2 * BN + hc * 64);
-          const float4* v1 = reinterpret_cast<const float4*>(kvb + 3 * BN + hc * 64);
+          const uint32_t k0 = kvb + (0 * BN + hc * 64) * 4, k1 = kvb + (1 * BN + hc * 64) * 4;
+          const uint32_t v0 = kvb + (2 * BN + hc * 64) * 4, v1 = kvb + (3 * BN + hc * 64) * 4;
           float s0a = 0.f, s0b = 0.f, s1a = 0.f, s1b = 0.f;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 a = k0[i], b = k1[i], c = k0[8 + i], d = k1[8 + i];
+            const float4 a = lds_v4(k0 + i * 16), b = lds_v4(k1 + i * 16), c = lds_v4(k0 + (8 + i) * 16), d = lds_v4(k1 + (8 + i) * 16);
             const float x0 = __uint_as_float(qa[4 * i]), x1 = __uint_as_float(qa[4 * i + 1]);
             const float x2 = __uint_as_float(qa[4 * i + 2]), x3 = __uint_as_float(qa[4 * i + 3]);
             const float y0 = __uint_as_float(qb[4 * i]), y1 = __uint_as_float(qb[4 * i + 1]);
@@ -333,7 +356,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint32_t o[32];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 a = v0[half * 8 + i], b = v1[half * 8 + i];
+              const float4 a = lds_v4(v0 + (half * 8 + i) * 16), b = lds_v4(v1 + (half * 8 + i) * 16);
               o[4 * i] = __float_as_uint(p0 * a.x + p1 * b.x);
               o[4 * i + 1] = __float_as_uint(p0 * a.y + p1 * b.y);
               o[4 * i + 2] = __float_as_uint(p0 * a.z + p1 * b.z);
