@@ -170,7 +170,8 @@ static int ensure_cond(tld_denoiser* h, int rows) {
   if (h->ycond) cudaFree(h->ycond);
   if (h->kv) cudaFree(h->kv);
   if (h->tlevels) cudaFree(h->tlevels);
-  h->ycond = nullptr; h->kv = nullptr; h->tlevels = nullptr;
+  if (h->cond_scratch) cudaFree(h->cond_scratch);
+  h->ycond = nullptr; h->kv = nullptr; h->tlevels = nullptr; h->cond_scratch = nullptr;
   if (h->graph_exec) {
     cudaGraphExecDestroy(h->graph_exec);
     h->graph_exec = nullptr;
@@ -180,6 +181,7 @@ static int ensure_cond(tld_denoiser* h, int rows) {
   if (dev_alloc(h, &h->ycond, (long long)r * h->D, false)) return 1;
   if (dev_alloc(h, &h->kv, (long long)r * h->L * 2 * h->D, false)) return 1;
   if (dev_alloc(h, &h->tlevels, r, false)) return 1;
+  if (dev_alloc(h, &h->cond_scratch, (long long)r * (h->E + 2 * h->D), false)) return 1;
   h->ws_cond_rows = r;
   return 0;
 }
@@ -307,7 +309,7 @@ void tld_denoiser_destroy(tld_denoiser* h) {
   cudaDeviceSynchronize();
   free_workspace(h);
   for (void* p : h->allocs) cudaFree(p);
-  void* extra[] = {h->ycond, h->kv, h->tlevels, h->x_t, h->x0_prev, h->x0_out, h->step_table};
+  void* extra[] = {h->ycond, h->kv, h->tlevels, h->cond_scratch, h->x_t, h->x0_prev, h->x0_out, h->step_table};
   for (void* p : extra)
     if (p) cudaFree(p);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -360,8 +362,9 @@ int tld_denoiser_forward(tld_denoiser* h, const float* x, const float* noise_lev
   if (ensure_workspace(h, batch) || ensure_cond(h, 2 * batch)) return 1;
   const long long kvs = (long long)h->L * 2 * h->D;
   // conditioning tokens: rows [0,B) noise token, rows [B,2B) label token (denoiser.py:117-122)
-  if (launch_cond_noise(noise_level, batch, h->E, h->D, h->cond, h->ycond, st)) return 1;
-  if (launch_cond_label(label, batch, batch, h->Te, h->D, h->cond, h->ycond + (size_t)batch * h->D, st)) return 1;
+  if (launch_cond_noise(noise_level, batch, h->E, h->D, h->cond, h->ycond, h->cond_scratch, st)) return 1;
+  if (launch_cond_label(label, batch, batch, h->Te, h->D, h->cond, h->ycond + (size_t)batch * h->D, h->cond_scratch, st))
+    return 1;
   // K|V of both cond tokens for every layer in one GEMM (transformer_blocks.py:71)
   if (launch_gemm(EPI_F32, h->ycond, h->D, h->wkv_all, h->D, 2 * batch, int(kvs), h->D, h->kv, int(kvs), nullptr,
                   nullptr, st))
@@ -454,8 +457,9 @@ int tld_sampler_generate(tld_denoiser* h, const float* labels, const float* seed
   // ---- conditioning hoisted out of the loop: the noise token depends only on the step, the label token only
   // on the sample.  rows [0,calls): noise tokens; rows [calls, calls+2B): label tokens.
   const long long kvs = (long long)h->L * 2 * h->D;
-  if (launch_cond_noise(h->tlevels, calls, h->E, h->D, h->cond, h->ycond, st)) return 1;
-  if (launch_cond_label(labels, Beff, num_imgs, h->Te, h->D, h->cond, h->ycond + (size_t)calls * h->D, st)) return 1;
+  if (launch_cond_noise(h->tlevels, calls, h->E, h->D, h->cond, h->ycond, h->cond_scratch, st)) return 1;
+  if (launch_cond_label(labels, Beff, num_imgs, h->Te, h->D, h->cond, h->ycond + (size_t)calls * h->D, h->cond_scratch, st))
+    return 1;
   if (launch_gemm(EPI_F32, h->ycond, h->D, h->wkv_all, h->D, calls + Beff, int(kvs), h->D, h->kv, int(kvs), nullptr,
                   nullptr, st))
     return 1;

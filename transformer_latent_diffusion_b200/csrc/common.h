@@ -83,10 +83,11 @@ struct CondSave {  // optional fp32 intermediates kept for the backward pass (tr
   float* pre;  // [R, D]  W2 h1 + b2 (pre-LayerNorm)
 };
 // noise token: y[r] = LN(W2 gelu(W1 sincos(t[r]) + b1) + b2)  -> bf16 [R, D]
-int launch_cond_noise(const float* t, int R, int E, int D, const CondW& w, bf16* y, cudaStream_t st,
+// scratch: fp32 [R, E + 2 D] for the MLP intermediates (unused parts when sv supplies the buffers)
+int launch_cond_noise(const float* t, int R, int E, int D, const CondW& w, bf16* y, float* scratch, cudaStream_t st,
                       const CondSave* sv = nullptr);
 // label token: y[r] = LN(Wl label[r] + bl); label == nullptr or r >= R_real -> zero label (uncond half)
-int launch_cond_label(const float* label, int R, int R_real, int Te, int D, const CondW& w, bf16* y,
+int launch_cond_label(const float* label, int R, int R_real, int Te, int D, const CondW& w, bf16* y, float* scratch,
                       cudaStream_t st, float* pre_save = nullptr);
 // g = gelu(dwconv3x3(h) + b) over the token grid; h,g bf16 [B, grid, grid, C]; w tap-major [9, C]
 int launch_dwconv_gelu(const bf16* h, const float* w9, const float* bias, bf16* g, int B, int grid, int C,

@@ -55,6 +55,7 @@ struct tld_denoiser {
   bf16* ycond = nullptr;    // [rows, D]
   float* kv = nullptr;      // [rows, L*2D]
   float* tlevels = nullptr; // [max steps]
+  float* cond_scratch = nullptr;  // [rows, E + 2 D] fp32 intermediates of the conditioning MLP (inference path)
 
   // sampler state
   cudaStream_t own_stream = nullptr;

@@ -200,25 +200,46 @@ int launch_embed(const float* x, int Bx, int Bout, int C, int img, int patch, in
 }
 
 // --------------------------------------------------------------------------------------------
-// Conditioning tokens (denoiser.py:117-122, transformer_blocks.py:17-21).  One 256-thread block per row.
-// The sinusoid and both MLP layers are fp32 on purpose (bf16 sin(6283 t) is garbage).
-// Dense layers: one warp per output feature, lanes stride the (coalesced) weight row, warp reduce.
+// Conditioning tokens (denoiser.py:117-122, transformer_blocks.py:17-21).  The sinusoid and both MLP layers are fp32
+// on purpose (bf16 sin(6283 t) is garbage).  All R rows go through each layer together: a 16x16-tiled
+// fp32 dense kernel reads every weight once per 16 rows (the first version ran one CTA per row and re-streamed the
+// 3 MB of MLP weights R times: 0.5 ms for 128 rows), then one CTA per row does the LayerNorm -> bf16.
 // --------------------------------------------------------------------------------------------
-__device__ void block_dense(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ in,
-                            float* __restrict__ outv, int n_out, int n_in, bool gelu, float* __restrict__ pre_out = nullptr) {
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int o = wib; o < n_out; o += nw) {
-    const float* wr = W + (size_t)o * n_in;
-    float acc = 0.f;
-    for (int i = lane; i < n_in; i += 32) acc += __ldg(wr + i) * in[i];
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      acc += bias[o];
-      if (pre_out) pre_out[o] = acc;
-      outv[o] = gelu ? gelu_erf(acc) : acc;
-    }
+__global__ void __launch_bounds__(256) cond_sincos_kernel(const float* __restrict__ t, const float* __restrict__ speeds,
+                                                          float* __restrict__ emb, int R, int E) {
+  const int i = blockIdx.x * 256 + threadIdx.x, half = E / 2;
+  if (i >= R * half) return;
+  const int r = i / half, j = i % half;
+  const float a = speeds[j] * t[r];  // fp32 product, as the reference's fp32 path
+  emb[(size_t)r * E + j] = sinf(a);
+  emb[(size_t)r * E + half + j] = cosf(a);
+}
+
+// out[r, o] = act(bias[o] + sum_i in[r, i] W[o, i]);  in == nullptr or r >= R_real: zero input row.  pre (optional) keeps the
+// value before the activation.  16 rows x 16 outputs per CTA, K walked in 16-wide smem tiles.
+__global__ void __launch_bounds__(256) cond_dense_kernel(const float* __restrict__ in, int R, int R_real,
+                                                         const float* __restrict__ W, const float* __restrict__ bias,
+                                                         float* __restrict__ out, float* __restrict__ pre, int n_out,
+                                                         int n_in, int gelu) {
+  __shared__ float sA[16][17], sW[16][17];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int r = blockIdx.y * 16 + ty, o = blockIdx.x * 16 + tx;
+  const int rl = blockIdx.y * 16 + ty, ol = blockIdx.x * 16 + ty;   // rows of the two tiles this thread loads
+  float acc = 0.f;
+  for (int k0 = 0; k0 < n_in; k0 += 16) {
+    const int k = k0 + tx;
+    sA[ty][tx] = (in != nullptr && rl < R_real && k < n_in) ? in[(size_t)rl * n_in + k] : 0.f;
+    sW[ty][tx] = (ol < n_out && k < n_in) ? __ldg(W + (size_t)ol * n_in + k) : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc = fmaf(sA[ty][q], sW[tx][q], acc);
+    __syncthreads();
   }
-  __syncthreads();
+  if (r < R && o < n_out) {
+    acc += bias[o];
+    if (pre) pre[(size_t)r * n_out + o] = acc;
+    out[(size_t)r * n_out + o] = gelu ? gelu_erf(acc) : acc;
+  }
 }
 
 __device__ void block_layernorm_store(const float* __restrict__ v, const float* __restrict__ gw,
@@ -244,61 +265,36 @@ __device__ void block_layernorm_store(const float* __restrict__ v, const float* 
   for (int i = threadIdx.x; i < D; i += blockDim.x) y[i] = __float2bfloat16((v[i] - mu) * rstd * gw[i] + gb[i]);
 }
 
-__global__ void __launch_bounds__(256) cond_noise_kernel(const float* __restrict__ t, int E, int D, CondW w,
-                                                         bf16* __restrict__ y, CondSave sv) {
-  extern __shared__ float sm[];  // [E] sincos | [D] h1 | [D] h2 | [8] red
-  float* emb = sm;
-  float* h1 = sm + E;
-  float* h2 = h1 + D;
-  float* red = h2 + D;
+__global__ void __launch_bounds__(256) cond_ln_kernel(const float* __restrict__ pre, const float* __restrict__ gw,
+                                                      const float* __restrict__ gb, bf16* __restrict__ y, int D) {
+  __shared__ float red[8];
   const int r = blockIdx.x;
-  const float tv = t[r];
-  for (int i = threadIdx.x; i < E / 2; i += blockDim.x) {
-    const float a = w.speeds[i] * tv;  // fp32 product, as the reference's fp32 path
-    emb[i] = sinf(a);
-    emb[E / 2 + i] = cosf(a);
-  }
-  __syncthreads();
-  block_dense(w.w1, w.b1, emb, h1, D, E, true, sv.a1 ? sv.a1 + (size_t)r * D : nullptr);
-  block_dense(w.w2, w.b2, h1, h2, D, D, false);
-  if (sv.emb) {  // training: keep what the backward pass needs
-    for (int i = threadIdx.x; i < E; i += blockDim.x) sv.emb[(size_t)r * E + i] = emb[i];
-    for (int i = threadIdx.x; i < D; i += blockDim.x) {
-      sv.h1[(size_t)r * D + i] = h1[i];
-      sv.pre[(size_t)r * D + i] = h2[i];
-    }
-  }
-  block_layernorm_store(h2, w.ln_w, w.ln_b, y + (size_t)r * D, D, red);
+  block_layernorm_store(pre + (size_t)r * D, gw, gb, y + (size_t)r * D, D, red);
 }
 
-__global__ void __launch_bounds__(256) cond_label_kernel(const float* __restrict__ label, int R_real, int Te, int D,
-                                                         CondW w, bf16* __restrict__ y, float* __restrict__ pre_save) {
-  extern __shared__ float sm[];  // [Te] label | [D] proj | [8] red
-  float* lab = sm;
-  float* proj = sm + Te;
-  float* red = proj + D;
-  const int r = blockIdx.x;
-  const bool real = label != nullptr && r < R_real;
-  for (int i = threadIdx.x; i < Te; i += blockDim.x) lab[i] = real ? label[(size_t)r * Te + i] : 0.f;
-  __syncthreads();
-  block_dense(w.wl, w.bl, lab, proj, D, Te, false);
-  if (pre_save)
-    for (int i = threadIdx.x; i < D; i += blockDim.x) pre_save[(size_t)r * D + i] = proj[i];
-  block_layernorm_store(proj, w.ln_w, w.ln_b, y + (size_t)r * D, D, red);
-}
-
-int launch_cond_noise(const float* t, int R, int E, int D, const CondW& w, bf16* y, cudaStream_t st, const CondSave* sv) {
+int launch_cond_noise(const float* t, int R, int E, int D, const CondW& w, bf16* y, float* scratch, cudaStream_t st,
+                      const CondSave* sv) {
   if (R <= 0) return 0;
-  const size_t smem = (size_t)(E + 2 * D + 8) * sizeof(float);
-  cond_noise_kernel<<<R, 256, smem, st>>>(t, E, D, w, y, sv ? *sv : CondSave{nullptr, nullptr, nullptr, nullptr});
+  TLD_CHECK(scratch != nullptr || (sv && sv->emb && sv->a1 && sv->h1 && sv->pre), "cond_noise: no scratch buffer");
+  float* emb = (sv && sv->emb) ? sv->emb : scratch;
+  float* h1 = (sv && sv->h1) ? sv->h1 : scratch + (size_t)R * E;
+  float* pre = (sv && sv->pre) ? sv->pre : scratch + (size_t)R * (E + D);
+  cond_sincos_kernel<<<(R * (E / 2) + 255) / 256, 256, 0, st>>>(t, w.speeds, emb, R, E);
+  const dim3 grid((D + 15) / 16, (R + 15) / 16);
+  cond_dense_kernel<<<grid, 256, 0, st>>>(emb, R, R, w.w1, w.b1, h1, sv ? sv->a1 : nullptr, D, E, 1);
+  cond_dense_kernel<<<grid, 256, 0, st>>>(h1, R, R, w.w2, w.b2, pre, nullptr, D, D, 0);
+  cond_ln_kernel<<<R, 256, 0, st>>>(pre, w.ln_w, w.ln_b, y, D);
   TLD_CUDA_OK(cudaGetLastError());
   return 0;
 }
-int launch_cond_label(const float* label, int R, int R_real, int Te, int D, const CondW& w, bf16* y,
+int launch_cond_label(const float* label, int R, int R_real, int Te, int D, const CondW& w, bf16* y, float* scratch,
                       cudaStream_t st, float* pre_save) {
   if (R <= 0) return 0;
-  const size_t smem = (size_t)(Te + D + 8) * sizeof(float);
-  cond_label_kernel<<<R, 256, smem, st>>>(label, R_real, Te, D, w, y, pre_save);
+  TLD_CHECK(scratch != nullptr || pre_save != nullptr, "cond_label: no scratch buffer");
+  float* pre = pre_save ? pre_save : scratch;
+  const dim3 grid((D + 15) / 16, (R + 15) / 16);
+  cond_dense_kernel<<<grid, 256, 0, st>>>(label, R, label ? R_real : 0, w.wl, w.bl, pre, nullptr, D, Te, 0);
+  cond_ln_kernel<<<R, 256, 0, st>>>(pre, w.ln_w, w.ln_b, y, D);
   TLD_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -268,8 +268,10 @@ TLD_API int tld_train_forward(tld_denoiser* h, const float* x, const float* nois
   float* s_label = h->t_small;  // [B, Te] copy of the labels for the label_proj wgrad
   TLD_CUDA_OK(cudaMemcpyAsync(s_label, label, sizeof(float) * (size_t)B * h->Te, cudaMemcpyDeviceToDevice, st));
   CondSave cs{h->t_cond_emb, h->t_cond_a1, h->t_cond_h1, h->t_cond_pre};
-  if (launch_cond_noise(noise_level, B, h->E, D, h->cond, h->ycond, st, &cs)) return 1;
-  if (launch_cond_label(label, B, B, h->Te, D, h->cond, h->ycond + (size_t)B * D, st, h->t_cond_pre + (size_t)B * D)) return 1;
+  if (launch_cond_noise(noise_level, B, h->E, D, h->cond, h->ycond, h->cond_scratch, st, &cs)) return 1;
+  if (launch_cond_label(label, B, B, h->Te, D, h->cond, h->ycond + (size_t)B * D, h->cond_scratch, st,
+                        h->t_cond_pre + (size_t)B * D))
+    return 1;
   if (launch_gemm(EPI_F32, h->ycond, D, h->wkv_all, D, 2 * B, int(kvs), D, h->kv, int(kvs), nullptr, nullptr, st)) return 1;
   float* sm = h->t_small + (size_t)B * h->Te;
   EmbedSave es{sm, sm + (size_t)T * h->pd, sm + 2 * (size_t)T * h->pd, sm + 6 * (size_t)T * h->pd};
