@@ -186,7 +186,7 @@ def time_dominant_gemm(lib, peaks) -> dict:
     return {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel<BN=256,EPI_BIAS_BF16,CTAS=2> (mlp.0 up-projection, M=32768 N=3072 K=768, CTA-pair tiles)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": src,
             "ms_per_launch": ms, "flops_per_launch": flops,
-            "traffic": 200.9e6,  # dram read+write per launch from profiles/r01_gemm_ncu.txt (ncu --set full)
+            "traffic": 199.2e6,  # dram read+write per launch (55.1 + 144.1 MB) from profiles/r01_block_kernels_ncu.txt (ncu --set full)
             "method": "CUDA events around 20 back-to-back launches on the launch stream, 4 rotating operand sets (>L2)"}
 
 
