@@ -61,14 +61,17 @@ int launch_transpose_bf16(const bf16* in, bf16* outT, int R, int C, cudaStream_t
 // ------------------------------------------------------------------------------------------------
 // column sums: out[c] (+)= sum_r in[r, c]; deterministic (fixed row partition, fixed reduction order)
 // ------------------------------------------------------------------------------------------------
+// Two passes: partial[chunk][c] over a fixed row partition (grid = column groups x row chunks, so a [8192 x 768] input
+// runs on 24 x 64 CTAs instead of 24), then a fixed-order sum over the chunks.
 template <typename TIn>
-__global__ void __launch_bounds__(256) colsum_kernel(const TIn* __restrict__ in, float* __restrict__ out, int R, int C,
-                                                     int accumulate) {
+__global__ void __launch_bounds__(256) colsum_kernel(const TIn* __restrict__ in, float* __restrict__ partial, int R, int C,
+                                                     int rows_per_chunk) {
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * rows_per_chunk, r1 = min(R, r0 + rows_per_chunk);
   float s = 0.f;
   if (c < C)
-    for (int r = rl; r < R; r += 8) {
+    for (int r = r0 + rl; r < r1; r += 8) {
       if constexpr (sizeof(TIn) == 4) s += in[(size_t)r * C + c];
       else s += __bfloat162float(in[(size_t)r * C + c]);
     }
@@ -78,18 +81,44 @@ __global__ void __launch_bounds__(256) colsum_kernel(const TIn* __restrict__ in,
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    out[c] = accumulate ? out[c] + t : t;
+    partial[(size_t)blockIdx.y * C + c] = t;
   }
 }
-int launch_colsum_f32(const float* in, float* out, int R, int C, int accumulate, cudaStream_t st) {
-  colsum_kernel<float><<<(C + 31) / 32, 256, 0, st>>>(in, out, R, C, accumulate);
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                            int nchunk, int C, int accumulate) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  float t = 0.f;
+  for (int k = 0; k < nchunk; ++k) t += partial[(size_t)k * C + c];
+  out[c] = accumulate ? out[c] + t : t;
+}
+static float* g_colsum_partial = nullptr;
+static size_t g_colsum_cap = 0;
+template <typename TIn>
+static int colsum_launch(const TIn* in, float* out, int R, int C, int accumulate, cudaStream_t st) {
+  int nchunk = (R + 127) / 128;
+  if (nchunk > 64) nchunk = 64;
+  if (nchunk < 1) nchunk = 1;
+  const int rpc = (((R + nchunk - 1) / nchunk) + 7) / 8 * 8;
+  nchunk = (R + rpc - 1) / rpc;
+  if (nchunk < 1) nchunk = 1;
+  const size_t need = (size_t)nchunk * C;
+  if (need > g_colsum_cap) {
+    if (g_colsum_partial) cudaFree(g_colsum_partial);
+    TLD_CUDA_OK(cudaMalloc(&g_colsum_partial, need * sizeof(float)));
+    g_colsum_cap = need;
+  }
+  colsum_kernel<TIn><<<dim3((C + 31) / 32, nchunk), 256, 0, st>>>(in, g_colsum_partial, R, C, rpc);
+  TLD_CUDA_OK(cudaGetLastError());
+  colsum_reduce_kernel<<<(C + 255) / 256, 256, 0, st>>>(g_colsum_partial, out, nchunk, C, accumulate);
   TLD_CUDA_OK(cudaGetLastError());
   return 0;
 }
+int launch_colsum_f32(const float* in, float* out, int R, int C, int accumulate, cudaStream_t st) {
+  return colsum_launch<float>(in, out, R, C, accumulate, st);
+}
 int launch_colsum_bf16(const bf16* in, float* out, int R, int C, int accumulate, cudaStream_t st) {
-  colsum_kernel<bf16><<<(C + 31) / 32, 256, 0, st>>>(in, out, R, C, accumulate);
-  TLD_CUDA_OK(cudaGetLastError());
-  return 0;
+  return colsum_launch<bf16>(in, out, R, C, accumulate, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -349,7 +378,7 @@ int launch_dwconv_gelu_bwd(const bf16* hid, const bf16* dg, const float* w9, con
   dwconv_bwd_kernel<<<blocks, 256, 0, st>>>(du_tmp, nullptr, w9, bias, dhid, B, G, C, 1);
   TLD_CUDA_OK(cudaGetLastError());
   const long long total = (long long)B * G * G;
-  int nchunk = (int)((total + 255) / 256);
+  int nchunk = (int)((total + 31) / 32);   // >= 32 positions per chunk, at most 256 chunks (12 x 256 CTAs at C = 3072)
   if (nchunk > 256) nchunk = 256;
   const int ppc = (int)((total + nchunk - 1) / nchunk);
   nchunk = (int)((total + ppc - 1) / ppc);
