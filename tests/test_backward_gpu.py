@@ -51,7 +51,7 @@ def test_layernorm_backward(lib, rows, D):
     assert rel_fro(dw, w.grad) < 1e-4 and rel_fro(db, b.grad) < 1e-4
 
 
-@pytest.mark.parametrize("B,G,C", [(2, 8, 512), (3, 16, 1024), (1, 32, 256)])
+@pytest.mark.parametrize("B,G,C", [(2, 8, 512), (3, 16, 1024), (2, 16, 3072), (1, 32, 256)])
 def test_dwconv_gelu_backward(lib, B, G, C):
     g = torch.Generator(device="cuda").manual_seed(G + C)
     h = torch.randn(B, G, G, C, device="cuda", generator=g).bfloat16()

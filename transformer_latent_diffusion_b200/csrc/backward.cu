@@ -373,10 +373,15 @@ int launch_dwconv_gelu_bwd(const bf16* hid, const bf16* dg, const float* w9, con
   TLD_CHECK(C % 8 == 0, "dwconv_bwd: channels must be a multiple of 8");
   const long long threads = (long long)B * G * G * (C / 8);
   const unsigned blocks = (unsigned)((threads + 255) / 256);
-  dwconv_bwd_kernel<<<blocks, 256, 0, st>>>(hid, dg, w9, bias, du_tmp, B, G, C, 0);
-  TLD_CUDA_OK(cudaGetLastError());
-  dwconv_bwd_kernel<<<blocks, 256, 0, st>>>(du_tmp, nullptr, w9, bias, dhid, B, G, C, 1);
-  TLD_CUDA_OK(cudaGetLastError());
+  if (G == 16 && C % 64 == 0 && B <= 65535) {  // the 256-px model: shared-memory tile kernel (rowwise.cu)
+    if (launch_dwconv_g16_bwd(hid, dg, w9, bias, du_tmp, B, C, 1, st)) return 1;
+    if (launch_dwconv_g16_bwd(du_tmp, nullptr, w9, bias, dhid, B, C, 2, st)) return 1;
+  } else {
+    dwconv_bwd_kernel<<<blocks, 256, 0, st>>>(hid, dg, w9, bias, du_tmp, B, G, C, 0);
+    TLD_CUDA_OK(cudaGetLastError());
+    dwconv_bwd_kernel<<<blocks, 256, 0, st>>>(du_tmp, nullptr, w9, bias, dhid, B, G, C, 1);
+    TLD_CUDA_OK(cudaGetLastError());
+  }
   const long long total = (long long)B * G * G;
   int nchunk = (int)((total + 31) / 32);   // >= 32 positions per chunk, at most 256 chunks (12 x 256 CTAs at C = 3072)
   if (nchunk > 256) nchunk = 256;
@@ -427,11 +432,20 @@ __global__ void __launch_bounds__(256) xattn_bwd_kernel(const bf16* __restrict__
     const bf16* qr = q + row * D + head * 64;
     const float* gr = go + row * D + head * 64;
     float s0 = 0.f, s1 = 0.f, dp0 = 0.f, dp1 = 0.f;
-#pragma unroll 8
-    for (int d = 0; d < 64; ++d) {
-      const float qv = __bfloat162float(qr[d]), gv = gr[d];
-      s0 += qv * s_kv[0][d]; s1 += qv * s_kv[1][d];
-      dp0 += gv * s_kv[2][d]; dp1 += gv * s_kv[3][d];
+    // the row's 64 q values (128 B) and 64 upstream gradients (256 B) as 16-byte vector loads
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      const uint4 qv = *reinterpret_cast<const uint4*>(qr + v * 8);
+      const float4 g0 = *reinterpret_cast<const float4*>(gr + v * 8), g1 = *reinterpret_cast<const float4*>(gr + v * 8 + 4);
+      const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
+      const float gvv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int d = v * 8 + e;
+        const float qf = (e & 1) ? __uint_as_float(qw[e >> 1] & 0xffff0000u) : __uint_as_float(qw[e >> 1] << 16);
+        s0 += qf * s_kv[0][d]; s1 += qf * s_kv[1][d];
+        dp0 += gvv[e] * s_kv[2][d]; dp1 += gvv[e] * s_kv[3][d];
+      }
     }
     s0 *= scale; s1 *= scale;
     const float mx = fmaxf(s0, s1), e0 = __expf(s0 - mx), e1 = __expf(s1 - mx), inv = 1.f / (e0 + e1);
@@ -440,10 +454,15 @@ __global__ void __launch_bounds__(256) xattn_bwd_kernel(const bf16* __restrict__
     ds0 = p0 * (dp0 - dot) * scale;
     ds1 = p1 * (dp1 - dot) * scale;
     bf16* dqr = dq + row * D + head * 64;
-#pragma unroll 8
-    for (int d = 0; d < 64; d += 2) {
-      const float a = ds0 * s_kv[0][d] + ds1 * s_kv[1][d], c = ds0 * s_kv[0][d + 1] + ds1 * s_kv[1][d + 1];
-      *reinterpret_cast<uint32_t*>(dqr + d) = bw_pk2(a, c);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int d = v * 8 + 2 * e;
+        o[e] = bw_pk2(ds0 * s_kv[0][d] + ds1 * s_kv[1][d], ds0 * s_kv[0][d + 1] + ds1 * s_kv[1][d + 1]);
+      }
+      *reinterpret_cast<uint4*>(dqr + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
   s_row[tid][0] = ds0; s_row[tid][1] = ds1; s_row[tid][2] = p0; s_row[tid][3] = p1;

@@ -92,6 +92,9 @@ int launch_cond_label(const float* label, int R, int R_real, int Te, int D, cons
 // g = gelu(dwconv3x3(h) + b) over the token grid; h,g bf16 [B, grid, grid, C]; w tap-major [9, C]
 int launch_dwconv_gelu(const bf16* h, const float* w9, const float* bias, bf16* g, int B, int grid, int C,
                        cudaStream_t st);
+// 16x16-grid tile kernel in its backward modes: mode 1: out = second * gelu'(conv(in) + bias); mode 2: out = conv^T(in)
+int launch_dwconv_g16_bwd(const bf16* in, const bf16* second, const float* w9, const float* bias, bf16* out, int B, int C,
+                          int mode, cudaStream_t st);
 // tokens[B,N,D] fp32 -> Linear(D->pd)+bias -> unpatchify -> out[B,C,H,W] fp32
 int launch_outproj(const float* x, const float* w, const float* b, float* out, int B, int C, int img, int patch,
                    int D, cudaStream_t st);

@@ -421,6 +421,25 @@ __device__ __forceinline__ float2 gelu2(float2 v) {
   return ffma2(hv, e, hv);                                         // v/2 (1 + erf)
 }
 
+// d/dv gelu(v) = Phi(v) + v phi(v) on a channel pair (training backward): Phi through the same erf polynomial,
+// phi(v) = exp(-v^2/2) / sqrt(2 pi) on MUFU.EX2
+__device__ __forceinline__ float2 dgelu2(float2 v) {
+  const float2 vc = make_float2(fminf(fmaxf(v.x, -3.96f), 3.96f), fminf(fmaxf(v.y, -3.96f), 3.96f));
+  const float2 u = fmul2(vc, vc);
+  float2 r = ffma2(make_float2(-3.3440241686832906e-09f, -3.3440241686832906e-09f), u,
+                   make_float2(2.5340079901070567e-07f, 2.5340079901070567e-07f));
+  r = ffma2(r, u, make_float2(-8.418431207246613e-06f, -8.418431207246613e-06f));
+  r = ffma2(r, u, make_float2(0.00016371029778383672f, 0.00016371029778383672f));
+  r = ffma2(r, u, make_float2(-0.002110206289216876f, -0.002110206289216876f));
+  r = ffma2(r, u, make_float2(0.019370341673493385f, 0.019370341673493385f));
+  r = ffma2(r, u, make_float2(-0.13240252435207367f, -0.13240252435207367f));
+  r = ffma2(r, u, make_float2(0.7977136969566345f, 0.7977136969566345f));
+  const float2 cdf = ffma2(fmul2(vc, r), make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+  const float2 arg = fmul2(v, fmul2(v, make_float2(-0.72134752044448170f, -0.72134752044448170f)));
+  const float2 pdf = make_float2(ex2_approx(arg.x) * 0.3989422804014327f, ex2_approx(arg.y) * 0.3989422804014327f);
+  return ffma2(v, pdf, cdf);
+}
+
 // Specialised kernel for a compile-time token grid G (8/16/32/64): one thread = 4 channels (two FFMA2 pairs) of one
 // grid row, sliding along x.  y-borders: row index clamped + that tap row's weights zeroed (branch-free);
 // x-borders: zero columns.  Loads run 4 columns ahead of their use through a 6-deep raw-register ring.
@@ -511,10 +530,14 @@ __global__ void __launch_bounds__(256) dwconv_gelu_grid_kernel(const bf16* __res
 // [256 positions x 64 ch] bf16 slab (32 KB) arrives with ONE TMA load (128B swizzle); lane = channel pair, so every
 // warp-wide LDS reads one full 128-byte row (conflict-free); warp w produces grid rows 2w and 2w+1 sliding along x
 // with a 4-row x 3-column fp32 window.  All shared-memory offsets are compile-time constants after unrolling.
+// MODE 0: g = gelu(conv(h) + b)                         (forward)
+// MODE 1: out = second * gelu'(conv(h) + b)              (backward A: du = dg * gelu'(u), u recomputed)
+// MODE 2: out = conv^T(in): flipped taps, no bias        (backward B: dh = dwconv^T(du))
+template <int MODE>
 __global__ void __launch_bounds__(256) dwconv_gelu_g16_kernel(const __grid_constant__ CUtensorMap tmap_h,
                                                               const float* __restrict__ w9,
                                                               const float* __restrict__ bias, bf16* __restrict__ g,
-                                                              int C) {
+                                                              int C, const bf16* __restrict__ second) {
   constexpr int G = 16;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tile = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -533,8 +556,9 @@ __global__ void __launch_bounds__(256) dwconv_gelu_g16_kernel(const __grid_const
   const int ch = c0 + 2 * lane;
   float2 w[9];
 #pragma unroll
-  for (int tp = 0; tp < 9; ++tp) w[tp] = __ldg(reinterpret_cast<const float2*>(w9 + (size_t)tp * C + ch));
-  const float2 bs = __ldg(reinterpret_cast<const float2*>(bias + ch));
+  for (int tp = 0; tp < 9; ++tp)
+    w[tp] = __ldg(reinterpret_cast<const float2*>(w9 + (size_t)(MODE == 2 ? 8 - tp : tp) * C + ch));
+  const float2 bs = MODE == 2 ? make_float2(0.f, 0.f) : __ldg(reinterpret_cast<const float2*>(bias + ch));
   __syncthreads();  // barrier init visible before anyone polls it
   pdl_wait();       // every thread: the output buffer may still be read by an earlier kernel
   mbar_wait(bar, 0);
@@ -572,7 +596,20 @@ __global__ void __launch_bounds__(256) dwconv_gelu_g16_kernel(const __grid_const
         a0 = ffma2(w[dy * 3 + dx], win[(x + dx + 2) % 3][dy], a0);
         a1 = ffma2(w[dy * 3 + dx], win[(x + dx + 2) % 3][dy + 1], a1);
       }
-    const float2 g0 = gelu2(a0), g1 = gelu2(a1);
+    float2 g0, g1;
+    if constexpr (MODE == 0) {
+      g0 = gelu2(a0);
+      g1 = gelu2(a1);
+    } else if constexpr (MODE == 1) {
+      const bf16* sec = second + (out - g);
+      const float2 d0 = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(sec + (size_t)x * C)));
+      const float2 d1 = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(sec + (size_t)(G + x) * C)));
+      g0 = fmul2(d0, dgelu2(a0));
+      g1 = fmul2(d1, dgelu2(a1));
+    } else {
+      g0 = a0;
+      g1 = a1;
+    }
     *reinterpret_cast<uint32_t*>(out + (size_t)x * C) = pack_bf16x2_dev(g0.x, g0.y);
     *reinterpret_cast<uint32_t*>(out + (size_t)(G + x) * C) = pack_bf16x2_dev(g1.x, g1.y);
     if (x + 2 < G) {
@@ -595,7 +632,8 @@ int launch_dwconv_gelu(const bf16* h, const float* w9, const float* bias, bf16* 
     constexpr int smem = 1024 + 16 * 16 * 128 + 64;
     CUtensorMap th;
     if (make_tmap_2d(&th, h, false, (long long)B * 256, C, C, 256)) return 1;
-    return launch_pdl(dwconv_gelu_g16_kernel, dim3(C / 64, B), dim3(256), smem, st, th, w9, bias, g, C);
+    return launch_pdl(dwconv_gelu_g16_kernel<0>, dim3(C / 64, B), dim3(256), smem, st, th, w9, bias, g, C,
+                      (const bf16*)nullptr);
   }
   switch (grid) {
     case 8: dwconv_gelu_grid_kernel<8><<<blocks, 256, 0, st>>>(h, w9, bias, g, B, C); break;
@@ -606,6 +644,19 @@ int launch_dwconv_gelu(const bf16* h, const float* w9, const float* bias, bf16* 
   }
   TLD_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+// backward passes A and B of the MLP middle on the 16x16 grid (same tile kernel, other point-wise tail)
+int launch_dwconv_g16_bwd(const bf16* in, const bf16* second, const float* w9, const float* bias, bf16* out, int B, int C,
+                          int mode, cudaStream_t st) {
+  TLD_CHECK(C % 64 == 0 && B <= 65535 && (mode == 1 || mode == 2), "dwconv_g16_bwd: bad arguments");
+  constexpr int smem = 1024 + 16 * 16 * 128 + 64;
+  CUtensorMap th;
+  if (make_tmap_2d(&th, in, false, (long long)B * 256, C, C, 256)) return 1;
+  if (mode == 1)
+    return launch_pdl(dwconv_gelu_g16_kernel<1>, dim3(C / 64, B), dim3(256), smem, st, th, w9, bias, out, C, second);
+  return launch_pdl(dwconv_gelu_g16_kernel<2>, dim3(C / 64, B), dim3(256), smem, st, th, w9, bias, out, C,
+                    (const bf16*)nullptr);
 }
 
 // --------------------------------------------------------------------------------------------
