@@ -91,6 +91,10 @@ TLD_API int tld_sampler_last_stats(tld_denoiser* h, float* loop_ms, int64_t* ker
 /* out = A[M,K] * W[N,K]^T with epilogue `epi`: 0 bf16 | 1 +bias bf16 | 2 x_f32 += acc+bias | 4 f32 */
 TLD_API int tld_op_gemm(int epi, const uint16_t* A, const uint16_t* W, int M, int N, int K, void* out,
                 const float* bias, void* stream);
+/* C[M,N] = A^T B with A stored [K,M] and B stored [K,N] (bf16, row-major over K): the weight-gradient product
+ * dW = dY^T X of the training step (tld/train.py:169 via autograd) on MN-major tcgen05 operands, no transposed copies.
+ * epi 0: bf16 out, 4: fp32 out. */
+TLD_API int tld_op_gemm_mn(int epi, const uint16_t* A, const uint16_t* B, int M, int N, int K, void* out, void* stream);
 /* q-projection GEMM fused with the 2-key cross-attention and residual add (transformer_blocks.py:70-72,137):
  * x[M,D] += softmax2(q k0, q k1)(v0,v1) with q = A Wq^T; kv0/kv1 [rows, 2D] fp32 (K | V). */
 TLD_API int tld_op_gemm_xattn(const uint16_t* A, const uint16_t* Wq, int M, int D, float* x, const float* kv0,

@@ -71,6 +71,21 @@ def test_gemm_plain(lib, ctas, M, N, K, epi):
     assert err < tol, f"rel_fro={err:.3e}\n" + _err_map(out.float(), ref)
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (768, 3072, 1024), (3072, 768, 8192), (2304, 768, 520), (200, 128, 136),
+                                   (4096, 1024, 256)])
+def test_gemm_mn_major(lib, ctas, M, N, K):
+    """dW = dY^T X on MN-major operands (A [K,M], B [K,N] row-major): the wgrad shape, incl. ragged M and K."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = (torch.randn(K, M, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    B = torch.randn(K, N, device="cuda", generator=g).bfloat16()
+    ref = A.float().t() @ B.float()
+    out = torch.full((M, N), float("nan"), device="cuda")
+    lib.check(lib.load().tld_op_gemm_mn(4, lib.ptr(A), lib.ptr(B), M, N, K, lib.ptr(out), _stream()), "gemm_mn")
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all(), "non-finite / unwritten outputs\n" + _err_map(out.nan_to_num(1e9), ref)
+    assert rel_fro(out, ref) < 2e-5, _err_map(out, ref)
+
+
 @pytest.mark.parametrize("M,N,K", [(256, 1024, 256), (384, 3072, 768)])
 def test_gemm_bias_bf16(lib, ctas, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(1)

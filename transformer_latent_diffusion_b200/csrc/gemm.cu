@@ -200,6 +200,35 @@ int launch_gemm(int epi, const bf16* A, int lda, const bf16* W, int ldw, int M, 
   return dispatch(ctas, bn, epi, ta, tb, tc, M, N, K, ep, st);
 }
 
+// C[M,N] = A^T B, A stored [K, M] (row pitch lda), B stored [K, N] (row pitch ldb), both bf16; out fp32 (EPI_F32) or bf16
+// (EPI_BF16).  The weight-gradient shape dW = dY^T X: K = tokens, no transposed copies (see GemmEpi::mn_major).
+int launch_gemm_mn(int epi, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, void* out, int ldo,
+                   cudaStream_t st) {
+  TLD_CHECK(epi == EPI_F32 || epi == EPI_BF16, "launch_gemm_mn: only the plain fp32 / bf16 epilogues");
+  TLD_CHECK(M > 0 && N > 0 && K > 0, "launch_gemm_mn: empty problem");
+  TLD_CHECK(M % 8 == 0 && N % 64 == 0 && lda % 8 == 0 && ldb % 8 == 0,
+            "launch_gemm_mn: M/lda/ldb multiples of 8 and N a multiple of 64");
+  TLD_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+            "launch_gemm_mn: operands must be 16-byte aligned");
+  const bool out_f32 = epi == EPI_F32;
+  TLD_CHECK((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo * (out_f32 ? 4 : 2)) % 16 == 0,
+            "launch_gemm_mn: output must be 16-byte aligned with a 16-byte multiple row pitch");
+  // a CTA pair splits the N tile in two: each half must be whole 64-column atoms
+  int ctas = g_gemm_ctas ? g_gemm_ctas : (M >= 4096 ? 2 : 1);
+  int bn = pick_bn(M, N, ctas);
+  if (ctas == 2 && (bn / 2) % 64 != 0) {
+    ctas = 1;
+    bn = pick_bn(M, N, 1);
+  }
+  CUtensorMap ta, tb, tc;
+  if (make_tmap_2d(&ta, A, false, K, M, lda, 64)) return 1;   // box = 64 k-rows x 64 elements
+  if (make_tmap_2d(&tb, B, false, K, N, ldb, 64)) return 1;
+  if (make_tmap_2d(&tc, out, out_f32, M, N, ldo, 32)) return 1;
+  GemmEpi ep{};
+  ep.mn_major = 1;
+  return dispatch(ctas, bn, epi, ta, tb, tc, M, N, K, ep, st);
+}
+
 static int dispatch(int ctas, int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M,
                     int N, int K, const GemmEpi& ep, cudaStream_t st) {
   if (ctas == 2) {

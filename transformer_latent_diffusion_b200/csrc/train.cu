@@ -4,7 +4,7 @@
 //
 // Tensor-core work: every dgrad / wgrad is the tcgen05 GEMM of gemm_tcgen05.cuh on bf16 operands
 //   dgrad  dX[T,K]  = dY[T,N] * W[N,K]          -> launch_gemm(A = dY, W = W^T (kept transposed copy))
-//   wgrad  dW[N,K]  = dY^T[N,T] * X[T,K]        -> launch_gemm(A = dY^T, W = X^T)   (explicit bf16 transposes)
+//   wgrad  dW[N,K]  = dY^T[N,T] * X[T,K]        -> launch_gemm_mn(A = dY, B = X): MN-major operands, no transposes
 // Everything else is the HBM-bound kernels of backward.cu / attention_bwd.cu plus a few tiny fp32 products for the
 // 16-wide patch/out projections and the B-row conditioning path.  The residual-stream gradient stays fp32.
 #include "gemm_tcgen05.cuh"
@@ -222,9 +222,9 @@ static int ensure_train(tld_denoiser* h, int B) {
       return 1;
   }
   const long long kvs = 2LL * L * D;
-  if (talloc(h, &h->t_dx, T * D) || talloc(h, &h->t_dxn, T * D) || talloc(h, &h->t_a, T * D) || talloc(h, &h->t_aT, T * D) ||
-      talloc(h, &h->t_big, T * H4) || talloc(h, &h->t_bigT, T * H4) || talloc(h, &h->t_big2, T * H4) ||
-      talloc(h, &h->t_xnT, T * D) || talloc(h, &h->t_q, T * D) || talloc(h, &h->t_dkv, (long long)R8 * kvs) ||
+  if (talloc(h, &h->t_dx, T * D) || talloc(h, &h->t_dxn, T * D) || talloc(h, &h->t_a, T * D) ||
+      talloc(h, &h->t_big, T * H4) || talloc(h, &h->t_big2, T * H4) ||
+      talloc(h, &h->t_xnT, 2LL * 9 * H4) /* [9, H4] fp32 scratch of the depthwise tap gradients */ || talloc(h, &h->t_q, T * D) || talloc(h, &h->t_dkv, (long long)R8 * kvs) ||
       talloc(h, &h->t_cond_pre, 2LL * B * D) || talloc(h, &h->t_cond_h1, 1LL * B * D) || talloc(h, &h->t_cond_a1, 1LL * B * D) ||
       talloc(h, &h->t_cond_emb, 1LL * B * h->E))
     return 1;
@@ -333,22 +333,19 @@ TLD_API int tld_train_backward(tld_denoiser* h, const float* d_pred, int batch, 
     auto& t = h->tl[l];
     const std::string b = tb + "decoder_blocks." + std::to_string(l) + ".";
     // ================= MLPSepConv: x3 = x2 + conv1x1(gelu(dwconv(conv1x1(LN3 x2)))) =================
-    if (launch_cast_transpose_f32(h->t_dx, h->t_a, h->t_aT, T, D, st)) return 1;                     // dy (bf16), dy^T
+    if (launch_cast_transpose_f32(h->t_dx, h->t_a, nullptr, T, D, st)) return 1;                     // dy -> bf16
     if (launch_colsum_f32(h->t_dx, G(h, b + "mlp.mlp.3.bias"), T, D, 0, st)) return 1;
     if (launch_gemm(EPI_BF16, h->t_a, D, wt.wdownT, D, T, H4, D, h->t_big, H4, nullptr, nullptr, st)) return 1;   // d_hid2
-    if (launch_transpose_bf16(t.hid2, h->t_bigT, T, H4, st)) return 1;
-    if (launch_gemm(EPI_F32, h->t_aT, T, h->t_bigT, T, D, H4, T, G(h, b + "mlp.mlp.3.weight"), H4, nullptr, nullptr, st)) return 1;
-    float* dw9 = reinterpret_cast<float*>(h->t_xnT);  // [9, H4] scratch (t_xnT is free here)
+    if (launch_gemm_mn(EPI_F32, h->t_a, D, t.hid2, H4, D, H4, T, G(h, b + "mlp.mlp.3.weight"), H4, st)) return 1;  // dy^T hid2
+    float* dw9 = reinterpret_cast<float*>(h->t_xnT);  // [9, H4] scratch
     if (launch_dwconv_gelu_bwd(t.hid, h->t_big, ly.dww9, ly.dwb, h->t_big2, h->t_big, dw9, G(h, b + "mlp.mlp.1.bias"), B, h->G, H4,
                                st))
       return 1;
     transpose_f32_small_kernel<<<blocks(9LL * H4), 256, 0, st>>>(dw9, G(h, b + "mlp.mlp.1.weight"), 9, H4);  // [9,C] -> [C,9]
     TLD_CUDA_OK(cudaGetLastError());
     if (launch_colsum_bf16(h->t_big, G(h, b + "mlp.mlp.0.bias"), T, H4, 0, st)) return 1;
-    if (launch_transpose_bf16(h->t_big, h->t_bigT, T, H4, st)) return 1;                            // d_hid^T
     if (launch_layernorm_bf16(t.xs2, ly.ln3w, ly.ln3b, h->xn, T, D, st)) return 1;                  // recompute LN3(x2)
-    if (launch_transpose_bf16(h->xn, h->t_xnT, T, D, st)) return 1;
-    if (launch_gemm(EPI_F32, h->t_bigT, T, h->t_xnT, T, H4, D, T, G(h, b + "mlp.mlp.0.weight"), D, nullptr, nullptr, st)) return 1;
+    if (launch_gemm_mn(EPI_F32, h->t_big, H4, h->xn, D, H4, D, T, G(h, b + "mlp.mlp.0.weight"), D, st)) return 1;  // d_hid^T xn
     if (launch_gemm(EPI_F32, h->t_big, H4, wt.wupT, H4, T, D, H4, h->t_dxn, D, nullptr, nullptr, st)) return 1;      // d LN3 out
     if (launch_layernorm_bwd(h->t_dxn, t.xs2, ly.ln3w, h->t_dx, G(h, b + "norm3.weight"), G(h, b + "norm3.bias"), T, D, st)) return 1;
     // ================= cross-attention: x2 = x1 + CA(LN2 x1, y) =================
@@ -357,20 +354,14 @@ TLD_API int tld_train_backward(tld_denoiser* h, const float* d_pred, int batch, 
     if (launch_xattn_bwd(h->t_q, h->t_dx, h->kv + (size_t)l * 2 * D, h->kv + (size_t)B * kvs + (size_t)l * 2 * D, kvs, h->t_a,
                          h->t_dkv + (size_t)l * 2 * D, h->t_dkv + (size_t)B * kvs + (size_t)l * 2 * D, kvs, B, N, D, st))
       return 1;
-    if (launch_transpose_bf16(h->t_a, h->t_aT, T, D, st)) return 1;                                 // dq^T
-    if (launch_transpose_bf16(h->xn, h->t_xnT, T, D, st)) return 1;
-    if (launch_gemm(EPI_F32, h->t_aT, T, h->t_xnT, T, D, D, T, G(h, b + "cross_attention.q_linear.weight"), D, nullptr, nullptr, st))
-      return 1;
+    if (launch_gemm_mn(EPI_F32, h->t_a, D, h->xn, D, D, D, T, G(h, b + "cross_attention.q_linear.weight"), D, st)) return 1;  // dq^T xn
     if (launch_gemm(EPI_F32, h->t_a, D, wt.wqT, D, T, D, D, h->t_dxn, D, nullptr, nullptr, st)) return 1;
     if (launch_layernorm_bwd(h->t_dxn, t.xs1, ly.ln2w, h->t_dx, G(h, b + "norm2.weight"), G(h, b + "norm2.bias"), T, D, st)) return 1;
     // ================= self-attention: x1 = x0 + Attn(qkv(LN1 x0)) =================
     if (launch_self_attention_bwd(t.qkv, h->t_dx, t.xs0, t.xs1, h->t_big, B, N, D, st)) return 1;   // dqkv [T,3D]
-    if (launch_transpose_bf16(h->t_big, h->t_bigT, T, 3 * D, st)) return 1;
     if (launch_layernorm_bf16(t.xs0, ly.ln1w, ly.ln1b, h->xn, T, D, st)) return 1;
-    if (launch_transpose_bf16(h->xn, h->t_xnT, T, D, st)) return 1;
-    if (launch_gemm(EPI_F32, h->t_bigT, T, h->t_xnT, T, 3 * D, D, T, G(h, b + "self_attention.qkv_linear.weight"), D, nullptr, nullptr,
-                    st))
-      return 1;
+    if (launch_gemm_mn(EPI_F32, h->t_big, 3 * D, h->xn, D, 3 * D, D, T, G(h, b + "self_attention.qkv_linear.weight"), D, st))
+      return 1;                                                                                     // dqkv^T xn
     if (launch_gemm(EPI_F32, h->t_big, 3 * D, wt.wqkvT, 3 * D, T, D, 3 * D, h->t_dxn, D, nullptr, nullptr, st)) return 1;
     if (launch_layernorm_bwd(h->t_dxn, t.xs0, ly.ln1w, h->t_dx, G(h, b + "norm1.weight"), G(h, b + "norm1.bias"), T, D, st)) return 1;
   }
