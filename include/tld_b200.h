@@ -125,6 +125,12 @@ TLD_API int tld_vae_conv3x3(const uint16_t* x, const uint16_t* w, const float* b
                             int w_px, int cin, int cout, void* stream);
 /* nearest-neighbour 2x upsample, NHWC bf16: x [batch,h,w,channels] -> y [batch,2h,2w,channels] */
 TLD_API int tld_vae_upsample2x(const uint16_t* x, uint16_t* y, int batch, int h, int w, int channels, void* stream);
+/* Image post-processing on the device (tld/diffusion.py:185, tld/train.py:36): img [batch,3,h,w] in [-1,1] (fp32, or bf16 when
+ * is_bf16) -> ONE uint8 HWC grid out[GH, GW, 3] in torchvision.make_grid layout (min(ncol,batch) images per row, `pad`
+ * black pixels around each; GH = rows*(h+pad)+pad, GW = cols*(w+pad)+pad), value = trunc(clip((x+1)/2, 0, 1) * 255) as
+ * ToPILImage does.  Lets the caller copy 1 byte per sample to the host instead of 4. */
+TLD_API int tld_image_grid_u8(const void* img, int is_bf16, uint8_t* out, int batch, int h, int w, int ncol, int pad,
+                              void* stream);
 
 /* ---- training step (tld/train.py:160-170: pred = model(x_noisy, sigma, label); loss.backward()) ---------------
  * tld_train_forward == tld_denoiser_forward but keeps the activations; tld_train_backward turns d(loss)/d(pred) into

@@ -90,3 +90,48 @@ def test_training(tld, tmp_path):  # reference tests/test_diffuser.py:96-121
     np.save(data_config.val_path, torch.randn(8, model_cfg.denoiser_config.text_emb_size).numpy())
     ema = main(model_cfg, log_every=1)
     assert all(torch.isfinite(p).all() for p in ema.parameters())
+
+
+def test_training_eval_checkpoint_resume(tld, tmp_path):
+    """eval_gen + checkpoint save / resume of train.main (tld/train.py:23-40,92-102,140-158):
+    the checkpoint has the reference's keys, eval grids are written on rank 0, and a from_scratch=False run picks up
+    the EMA weights, the optimizer state and the step counter."""
+    from PIL.Image import Image
+
+    from transformer_latent_diffusion_b200.configs import DataConfig, ModelConfig, TrainConfig
+    from transformer_latent_diffusion_b200.train import eval_gen, main
+    from transformer_latent_diffusion_b200.vae import AutoencoderKLDecoder
+
+    data_config = DataConfig(latent_path=str(tmp_path / "latents.npy"), text_emb_path=str(tmp_path / "text_emb.npy"),
+                             val_path=str(tmp_path / "val_emb.npy"))
+    ckpt = str(tmp_path / "ckpt.pt")
+    tc = TrainConfig(n_epoch=1, batch_size=32, save_model=True, compile=False, use_wandb=False, model_name=ckpt,
+                     save_and_eval_every_iters=3)
+    model_cfg = ModelConfig(data_config=data_config, train_config=tc)
+    dc = model_cfg.denoiser_config
+    n = 160   # 5 steps of 32
+    np.save(data_config.latent_path, torch.randn(n, dc.n_channels, dc.image_size, dc.image_size).numpy())
+    np.save(data_config.text_emb_path, torch.randn(n, dc.text_emb_size).numpy())
+    np.save(data_config.val_path, torch.randn(8, dc.text_emb_size).numpy())
+    vae = AutoencoderKLDecoder().to(device="cuda", dtype=model_cfg.vae_cfg.vae_dtype)
+    ema = main(model_cfg, log_every=1, vae=vae, eval_dir=str(tmp_path))
+    assert main.last_global_step == 5
+    assert os.path.exists(tmp_path / "eval_step0.png") and os.path.exists(tmp_path / "eval_step3.png")
+    assert os.path.exists(tmp_path / "img.jpg")
+    sd = torch.load(ckpt, map_location="cpu")
+    assert set(sd) == {"model_ema", "opt_state", "global_step"} and sd["global_step"] == 3
+    assert list(sd["model_ema"].keys()) == list(ema.state_dict().keys())
+    # resume: the step counter continues and the run starts from the checkpoint's EMA weights
+    tc2 = TrainConfig(n_epoch=1, batch_size=32, save_model=False, compile=False, use_wandb=False, model_name=ckpt,
+                      from_scratch=False, lr=0.0, alpha=1.0)   # lr 0 and alpha 1: weights must stay the checkpoint's
+    ema2 = main(ModelConfig(data_config=data_config, train_config=tc2), log_every=1)
+    assert main.last_global_step == 3 + 5
+    for k, v in ema2.state_dict().items():
+        assert torch.equal(v.cpu(), sd["model_ema"][k]), k
+    # eval_gen on its own: reference signature, PIL image of the 2 x 8 grid
+    from transformer_latent_diffusion_b200.diffusion import DiffusionGenerator
+
+    img = eval_gen(DiffusionGenerator(ema2.eval(), vae, torch.device("cuda"), torch.float32),
+                   torch.randn(8, dc.text_emb_size, device="cuda"), dc.image_size, out_path=str(tmp_path / "g.png"))
+    side = dc.image_size * 8
+    assert isinstance(img, Image) and img.size == (8 * side + 9 * 4, 2 * side + 3 * 4)

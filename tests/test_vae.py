@@ -139,3 +139,19 @@ def test_decode_gpu_bf16_matches_oracle():
     # bf16 weights AND activations through ~35 conv/GroupNorm layers with random weights: a few percent
     (img,) = m.to(torch.bfloat16).decode(z.cuda())
     assert img.dtype == torch.float32 and rel_fro(img, ref) < 8e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,nrow", [(1, 8, 8, 1), (4, 16, 24, 2), (5, 32, 32, 3), (16, 64, 64, 8)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_image_grid_uint8_matches_reference_postprocessing(B, H, W, nrow, dtype):
+    """tld_image_grid_u8 == ToPILImage(make_grid((x + 1) / 2, nrow, padding=4).clip(0, 1)) bit for bit
+    (tld/diffusion.py:185, tld/train.py:36) - the uint8 grid is built on the device."""
+    from transformer_latent_diffusion_b200.diffusion import image_grid_uint8, make_image_grid
+
+    g = torch.Generator().manual_seed(B * 100 + H)
+    x = (torch.randn(B, 3, H, W, generator=g) * 0.8).to(dtype)
+    ref = (make_image_grid(x, nrow=nrow, padding=4).permute(1, 2, 0) * 255).to(torch.uint8).numpy()
+    got = image_grid_uint8(x.cuda(), nrow, 4)
+    assert got.shape == ref.shape and got.dtype == ref.dtype
+    assert (got == ref).all(), f"{(got != ref).sum()} of {got.size} bytes differ"

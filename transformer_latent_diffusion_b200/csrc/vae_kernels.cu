@@ -195,6 +195,58 @@ int launch_upsample2x(const bf16* x, bf16* y, int B, int H, int W, int C, cudaSt
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Image post-processing on the device (tld/diffusion.py:185 `to_pil(make_grid((out + 1) / 2, nrow, padding=4).clip(0, 1))`,
+// tld/train.py:36): decoded images [B,3,H,W] in [-1,1] -> ONE uint8 HWC grid (torchvision.make_grid layout: `ncol` per
+// row, `pad` black pixels around every image), value = trunc(clip((x + 1) / 2, 0, 1) * 255) exactly as
+// ToPILImage's mul(255).byte().  The host then copies 1 byte per sample instead of 4.
+// For bf16 inputs the (x + 1) / 2 is rounded to bf16 after each operation, as torch does on a bf16 tensor.
+// ------------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void __launch_bounds__(256) image_grid_u8_kernel(const TIn* __restrict__ img, uint8_t* __restrict__ out, int B, int H,
+                                                            int W, int ncol, int pad, int GH, int GW) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;   // over GH * GW pixels
+  if (i >= (long long)GH * GW) return;
+  const int gy = int(i / GW), gx = int(i % GW);
+  const int cell_h = H + pad, cell_w = W + pad;
+  const int r = (gy - pad) / cell_h, c = (gx - pad) / cell_w;
+  const int y = gy - pad - r * cell_h, x = gx - pad - c * cell_w;
+  const int b = r * ncol + c;
+  uint8_t v[3] = {0, 0, 0};
+  if (gy >= pad && gx >= pad && y < H && x < W && c < ncol && b < B) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float f;
+      if constexpr (sizeof(TIn) == 2) {
+        const bf16 t = __float2bfloat16(__bfloat162float(img[(((size_t)b * 3 + ch) * H + y) * W + x]) + 1.0f);
+        f = __bfloat162float(__float2bfloat16(__bfloat162float(t) * 0.5f));
+      } else {
+        f = (img[(((size_t)b * 3 + ch) * H + y) * W + x] + 1.0f) * 0.5f;
+      }
+      f = fminf(fmaxf(f, 0.f), 1.f);
+      v[ch] = (uint8_t)(f * 255.0f);
+    }
+  }
+  out[i * 3 + 0] = v[0];
+  out[i * 3 + 1] = v[1];
+  out[i * 3 + 2] = v[2];
+}
+
+int launch_image_grid_u8(const void* img, int is_bf16, uint8_t* out, int B, int H, int W, int ncol, int pad, cudaStream_t st) {
+  TLD_CHECK(B > 0 && H > 0 && W > 0 && ncol > 0 && pad >= 0, "image_grid_u8: bad shape");
+  const int nc = ncol < B ? ncol : B, nr = (B + nc - 1) / nc;
+  const int GH = nr * (H + pad) + pad, GW = nc * (W + pad) + pad;
+  const long long px = (long long)GH * GW;
+  const unsigned blocks = (unsigned)((px + 255) / 256);
+  if (is_bf16)
+    image_grid_u8_kernel<bf16><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(img), out, B, H, W, nc, pad, GH, GW);
+  else
+    image_grid_u8_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(img), out, B, H, W, nc, pad, GH, GW);
+  TLD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace tld
 
 extern "C" {
@@ -216,6 +268,10 @@ __attribute__((visibility("default"))) int tld_vae_conv3x3(const uint16_t* x, co
   return tld::launch_conv3x3(reinterpret_cast<const tld::bf16*>(x), reinterpret_cast<const tld::bf16*>(w), bias,
                              reinterpret_cast<tld::bf16*>(out), batch, h, w_px, cin, cout,
                              reinterpret_cast<cudaStream_t>(stream));
+}
+__attribute__((visibility("default"))) int tld_image_grid_u8(const void* img, int is_bf16, uint8_t* out, int batch, int h,
+                                                             int w, int ncol, int pad, void* stream) {
+  return tld::launch_image_grid_u8(img, is_bf16, out, batch, h, w, ncol, pad, reinterpret_cast<cudaStream_t>(stream));
 }
 __attribute__((visibility("default"))) int tld_vae_upsample2x(const uint16_t* x, uint16_t* y, int batch, int h, int w,
                                                               int channels, void* stream) {

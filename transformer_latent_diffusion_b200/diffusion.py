@@ -68,6 +68,16 @@ class DiffusionGenerator:
         return img, latent
 
     @torch.no_grad()
+    def generate_grid_uint8(self, labels: Tensor, nrow: int, padding: int = 4, scale_factor: int = 8, **generate_kwargs):
+        """Same sampling + decode as ``generate`` but the post-processing of tld/diffusion.py:185 / tld/train.py:36
+        (``make_grid((out + 1) / 2, nrow, padding).clip(0, 1)`` -> ``ToPILImage``) runs on the device
+        (``tld_image_grid_u8``) and only the finished uint8 HWC grid crosses PCIe: 1 byte per sample instead of 4
+        (SURVEY.md §8(f) rank 3).  Returns (numpy uint8 [GH, GW, 3], final latent on device)."""
+        latent = self.generate_latents(labels, **generate_kwargs)
+        img = self.vae.decode((latent * scale_factor).to(self.model_dtype))[0]
+        return image_grid_uint8(img, nrow, padding), latent
+
+    @torch.no_grad()
     def generate_latents(self, labels: Tensor, n_iter: int = 30, num_imgs: int = 16, class_guidance: float = 3,
                          seed: int = 10, img_size: int = 32, sharp_f: float = 0.1, bright_f: float = 0.1,
                          exponent: float = 1, seeds: Optional[Tensor] = None, noise_levels=None,
@@ -149,6 +159,27 @@ def make_image_grid(images: Tensor, nrow: int, padding: int = 4) -> Tensor:
     return grid.clip(0, 1)
 
 
+def image_grid_uint8(images: Tensor, nrow: int, padding: int = 4) -> np.ndarray:
+    """(B,3,H,W) in [-1,1] on the GPU -> uint8 [GH, GW, 3] numpy grid: bit-identical to
+    ``(make_image_grid(images, nrow, padding).permute(1, 2, 0) * 255).byte()`` but computed by one CUDA kernel before the
+    device-to-host copy."""
+    if not images.is_cuda:
+        raise _lib.TldError("image_grid_uint8: CUDA tensor required (no CPU fallback)")
+    if images.dtype not in (torch.float32, torch.bfloat16):
+        images = images.float()
+    images = images.contiguous()
+    B, Cc, H, W = images.shape
+    if Cc != 3:
+        raise ValueError("image_grid_uint8: expected RGB images [B,3,H,W]")
+    ncol = min(nrow, B)
+    nrows = -(-B // ncol)
+    out = torch.empty(nrows * (H + padding) + padding, ncol * (W + padding) + padding, 3, dtype=torch.uint8,
+                      device=images.device)
+    _lib.check(_lib.load().tld_image_grid_u8(_lib.ptr(images), int(images.dtype == torch.bfloat16), _lib.ptr(out), B, H, W,
+                                             ncol, padding, _lib.current_stream_ptr(images.device)), "tld_image_grid_u8")
+    return out.cpu().numpy()
+
+
 class DiffusionTransformer:
     """text -> image wrapper (tld/diffusion.py:143-186)."""
 
@@ -177,11 +208,9 @@ class DiffusionTransformer:
                                 "the CLIP ViT-L/14 tower is out of scope for this package")
         nrow = int(np.sqrt(num_imgs))
         labels = self.text_encoder([prompt] * num_imgs)
-        out, _ = self.diffuser.generate(labels=labels, num_imgs=num_imgs, img_size=self.diffuser.model.image_size,
-                                        class_guidance=class_guidance, seed=seed, n_iter=n_iter, exponent=1,
-                                        scale_factor=8, sharp_f=0, bright_f=0)
-        grid = make_image_grid(out, nrow=nrow, padding=4)
+        arr, _ = self.diffuser.generate_grid_uint8(labels, nrow=nrow, padding=4, scale_factor=8, num_imgs=num_imgs,
+                                                   img_size=self.diffuser.model.image_size, class_guidance=class_guidance,
+                                                   seed=seed, n_iter=n_iter, exponent=1, sharp_f=0, bright_f=0)
         from PIL import Image
 
-        arr = (grid.permute(1, 2, 0).numpy() * 255).astype(np.uint8)  # ToPILImage: mul(255).byte()
         return Image.fromarray(arr)

@@ -10,6 +10,9 @@
   the flattened gradients = what DDP does inside ``accelerator.backward``), logging goes to stdout.
   bf16 tensor-core operands with fp32 accumulation/master weights replace the reference's fp16 autocast + GradScaler
   (no loss scaling needed).
+* ``eval_gen`` (tld/train.py:23-40) and the checkpoint save / resume of ``main`` (tld/train.py:92-102,140-158) use the
+  reference's file layout ``{"model_ema", "opt_state", "global_step"}``, so a checkpoint written by either side loads in
+  the other.
 """
 from __future__ import annotations
 
@@ -75,6 +78,21 @@ def count_parameters_per_layer(model: nn.Module) -> None:
         print(f"{name}: {param.numel()} parameters")
 
 
+def eval_gen(diffuser, labels: Tensor, img_size: int, out_path: Optional[str] = None):
+    """Fixed-seed sample grid from the EMA weights (tld/train.py:23-40): every validation embedding twice, 16 images,
+    guidance 4.5, seed 10, 40 DPM-Solver++ steps, sharpness shift 0.1, 8 per row with 4 px padding.  Returns the PIL image
+    and saves it under the reference's file name (or ``out_path``)."""
+    from PIL import Image
+
+    class_guidance, seed = 4.5, 10
+    arr, _ = diffuser.generate_grid_uint8(torch.repeat_interleave(labels, 2, dim=0), nrow=8, padding=4, num_imgs=16,
+                                          class_guidance=class_guidance, seed=seed, n_iter=40, exponent=1, sharp_f=0.1,
+                                          img_size=img_size)       # (x+1)/2, clip, *255 -> uint8 on the device
+    img = Image.fromarray(arr)
+    img.save(out_path or f"emb_val_cfg:{class_guidance}_seed:{seed}.png")
+    return img
+
+
 def update_ema(ema_model: nn.Module, model: nn.Module, alpha: float = 0.999) -> None:
     """ema = alpha * ema + (1 - alpha) * param (tld/train.py:55-58), one fused foreach pass"""
     with torch.no_grad():
@@ -121,11 +139,20 @@ def train_step(model: nn.Module, optimizer, x: Tensor, x_noisy: Tensor, sigma: T
     return loss.detach()
 
 
-def main(config: ModelConfig, device: Optional[torch.device] = None, log_every: int = 50) -> nn.Module:
-    """Training loop with the reference's semantics (tld/train.py:62-176). Returns the EMA model (rank 0) / model."""
+def main(config: ModelConfig, device: Optional[torch.device] = None, log_every: int = 50, vae: Optional[nn.Module] = None,
+         eval_dir: Optional[str] = None) -> nn.Module:
+    """Training loop with the reference's semantics (tld/train.py:62-176). Returns the EMA model (rank 0) / model.
+
+    ``vae``: decoder used by the periodic ``eval_gen`` on rank 0 (the reference downloads it with
+    ``AutoencoderKL.from_pretrained``, tld/train.py:78 - no network here, so the caller injects it; without one the
+    evaluation images are skipped and only the checkpoint is written).  ``from_scratch=False`` resumes from
+    ``train_config.model_name`` exactly as tld/train.py:92-102 (EMA weights into the model, optimizer state, step)."""
+    import os
+
     import torch.distributed as dist
 
     from .denoiser import Denoiser
+    from .diffusion import DiffusionGenerator
 
     denoiser_config, train_config, dataconfig = config.denoiser_config, config.train_config, config.data_config
     rank = dist.get_rank() if dist.is_initialized() else 0
@@ -134,16 +161,27 @@ def main(config: ModelConfig, device: Optional[torch.device] = None, log_every: 
 
     latent_train_data = torch.tensor(np.load(dataconfig.latent_path), dtype=torch.float32)
     train_label_embeddings = torch.tensor(np.load(dataconfig.text_emb_path), dtype=torch.float32)
+    emb_val = None
+    if dataconfig.val_path and os.path.exists(dataconfig.val_path):
+        emb_val = torch.tensor(np.load(dataconfig.val_path), dtype=torch.float32).to(device)
     n = latent_train_data.shape[0]
     model = Denoiser(**asdict(denoiser_config)).to(device)
+    optimizer = torch.optim.Adam(model.parameters(), lr=train_config.lr)
+    global_step = 0
+    if not train_config.from_scratch:  # tld/train.py:92-102 (the wandb.restore download is the caller's business)
+        full_state_dict = torch.load(train_config.model_name, map_location=device)
+        model.load_state_dict(full_state_dict["model_ema"])
+        optimizer.load_state_dict(full_state_dict["opt_state"])
+        global_step = int(full_state_dict["global_step"])
     if world > 1:  # identical initial weights on every rank (DDP broadcasts rank 0's)
         for p in model.parameters():
             dist.broadcast(p.data, src=0)
-    optimizer = torch.optim.Adam(model.parameters(), lr=train_config.lr)
     ema_model = copy.deepcopy(model) if rank == 0 else None
+    diffuser = None
     if rank == 0:
         print(count_parameters(model))
-    global_step = 0
+        if vae is not None:
+            diffuser = DiffusionGenerator(ema_model, vae, device, torch.float32)
     gen = torch.Generator().manual_seed(1234 + rank)
     for epoch in range(1, train_config.n_epoch + 1):
         perm = torch.randperm(n, generator=torch.Generator().manual_seed(epoch))  # same shuffle on every rank
@@ -155,13 +193,24 @@ def main(config: ModelConfig, device: Optional[torch.device] = None, log_every: 
             noise = torch.randn(x.shape, generator=gen).to(device)
             mask = (torch.rand(y.size(0), generator=gen) < 0.15).to(device)
             xs, x_noisy, sigma, label = noise_batch(x, y, noise_level, noise, mask, config.vae_cfg.vae_scale_factor)
+            if global_step % train_config.save_and_eval_every_iters == 0:  # tld/train.py:140-158, before the step
+                if world > 1:
+                    dist.barrier()
+                if rank == 0:
+                    if diffuser is not None and emb_val is not None:
+                        ema_model.eval()
+                        out = eval_gen(diffuser, emb_val, denoiser_config.image_size,
+                                       out_path=os.path.join(eval_dir, f"eval_step{global_step}.png") if eval_dir else None)
+                        out.save(os.path.join(eval_dir, "img.jpg") if eval_dir else "img.jpg")
+                    if train_config.save_model and train_config.model_name:
+                        torch.save({"model_ema": ema_model.state_dict(), "opt_state": optimizer.state_dict(),
+                                    "global_step": global_step}, train_config.model_name)
             loss = train_step(model, optimizer, xs, x_noisy, sigma, label)
             if rank == 0:
                 update_ema(ema_model, model, alpha=train_config.alpha)
                 if global_step % log_every == 0:
                     print(f"epoch {epoch} step {global_step} train_loss {float(loss):.5f}")
-                if train_config.save_model and train_config.model_name and global_step % train_config.save_and_eval_every_iters == 0:
-                    torch.save({"model_ema": ema_model.state_dict(), "opt_state": optimizer.state_dict(),
-                                "global_step": global_step}, train_config.model_name)
             global_step += 1
+    if rank == 0:
+        main.last_global_step = global_step  # convenience for callers / tests (the reference keeps it local)
     return ema_model if rank == 0 else model
