@@ -129,6 +129,11 @@ TLD_API int tld_vae_upsample2x(const uint16_t* x, uint16_t* y, int batch, int h,
  * is_bf16) -> ONE uint8 HWC grid out[GH, GW, 3] in torchvision.make_grid layout (min(ncol,batch) images per row, `pad`
  * black pixels around each; GH = rows*(h+pad)+pad, GW = cols*(w+pad)+pad), value = trunc(clip((x+1)/2, 0, 1) * 255) as
  * ToPILImage does.  Lets the caller copy 1 byte per sample to the host instead of 4. */
+/* uint8 latent storage of the reference's dataset files (tld/data.py:51-60), bit-exact with the reference's arithmetic:
+ * quantize: out[i] = trunc(((clip(lat[i], -c, c) / c + 1) / 2) * 255), lat fp32 or (is_fp16) fp16 with per-step fp16 rounding;
+ * dequantize: out_fp16[i] = ((half(q[i]) / 255) * 2 - 1) * c, every step rounded to fp16. */
+TLD_API int tld_latent_quantize(const void* lat, int is_fp16, uint8_t* out, long long n, float clip_val, void* stream);
+TLD_API int tld_latent_dequantize(const uint8_t* q, uint16_t* out_fp16, long long n, float clip_val, void* stream);
 TLD_API int tld_image_grid_u8(const void* img, int is_bf16, uint8_t* out, int batch, int h, int w, int ncol, int pad,
                               void* stream);
 

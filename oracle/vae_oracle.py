@@ -70,3 +70,51 @@ def decode(sd, z, n_up_blocks=4, layers_per_block=2):
             x = conv(sd, f"decoder.up_blocks.{i}.upsamplers.0.conv", upsample_nearest2(x), 1)
     x = silu(group_norm(x, sd["decoder.conv_norm_out.weight"], sd["decoder.conv_norm_out.bias"]))
     return conv(sd, "decoder.conv_out", x, 1)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Encoder half (call sites tld/data.py:35-41,168).  Same status as the decoder: third-party
+# diffusers code, PARITY UNPINNED; restated from the published AutoencoderKL encoder (conv_in 3->128, four down blocks of
+# two ResNets with an asymmetric-pad stride-2 conv between them, mid block with one single-head attention,
+# GroupNorm/SiLU/conv_out to 2*latent channels, 1x1 quant_conv, diagonal Gaussian with logvar clamped to [-30, 20]).
+# ---------------------------------------------------------------------------------------------------------------
+def downsample(sd, name, x):
+    x = F.pad(x, (0, 1, 0, 1))  # diffusers Downsample2D with padding=0: pad right/bottom by one, then stride-2 conv
+    return F.conv2d(x, sd[name + ".weight"], sd[name + ".bias"], stride=2)
+
+
+def encode_moments(sd, x, n_down_blocks=4, layers_per_block=2):
+    """image x [B,3,H,W] in [-1,1] -> (mean, logvar) of the latent posterior, each [B,4,H/8,W/8]"""
+    h = conv(sd, "encoder.conv_in", x, 1)
+    for i in range(n_down_blocks):
+        for j in range(layers_per_block):
+            h = resnet(sd, f"encoder.down_blocks.{i}.resnets.{j}", h)
+        if i != n_down_blocks - 1:
+            h = downsample(sd, f"encoder.down_blocks.{i}.downsamplers.0.conv", h)
+    h = resnet(sd, "encoder.mid_block.resnets.0", h)
+    h = mid_attention(sd, "encoder.mid_block.attentions.0", h)
+    h = resnet(sd, "encoder.mid_block.resnets.1", h)
+    h = silu(group_norm(h, sd["encoder.conv_norm_out.weight"], sd["encoder.conv_norm_out.bias"]))
+    h = conv(sd, "encoder.conv_out", h, 1)
+    moments = conv(sd, "quant_conv", h, 0)
+    mean, logvar = moments.chunk(2, dim=1)
+    return mean, logvar.clamp(-30.0, 20.0)
+
+
+def gaussian_sample(mean, logvar, eps):
+    """DiagonalGaussianDistribution.sample with the noise injected: mean + exp(0.5 logvar) * eps"""
+    return mean + torch.exp(0.5 * logvar) * eps
+
+
+# uint8 latent storage of the reference's dataset files: restatement of tld/data.py:51-60 (checked against the reference's
+# own source in tests/golden/make_golden.py -> tests/golden/latent_quant.npz, so THIS part is pinned)
+def quantize_latents(lat, clip_val=20):
+    """latent -> byte: clip to [-clip_val, clip_val], map affinely onto [0, 255], truncate (tld/data.py:51-54)"""
+    unit = lat.clip(-clip_val, clip_val) / clip_val
+    return (255 * ((unit + 1) / 2)).to(torch.uint8)
+
+
+def dequantize_latents(q, clip_val=20):
+    """byte -> fp16 latent, every step rounded to fp16 as torch does on a half tensor (tld/data.py:57-60)"""
+    unit = 2 * (q.to(torch.float16) / 255) - 1
+    return clip_val * unit

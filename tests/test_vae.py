@@ -155,3 +155,119 @@ def test_image_grid_uint8_matches_reference_postprocessing(B, H, W, nrow, dtype)
     got = image_grid_uint8(x.cuda(), nrow, 4)
     assert got.shape == ref.shape and got.dtype == ref.dtype
     assert (got == ref).all(), f"{(got != ref).sum()} of {got.size} bytes differ"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# VAE encode + uint8 latent (de)quantisers (tld/data.py:34-60)
+# ------------------------------------------------------------------------------------------------------------------
+import os
+
+import numpy as np
+
+GOLD_Q = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "latent_quant.npz")
+
+
+def _small_encoder(block_out=(32, 64, 64, 64), seed=0):
+    from transformer_latent_diffusion_b200.vae import AutoencoderKLEncoder
+
+    torch.manual_seed(seed)
+    m = AutoencoderKLEncoder(block_out=block_out)
+    for k, p in m.named_parameters():
+        if p.ndim == 1:
+            p.data.add_(0.1 * torch.randn_like(p))
+    return m
+
+
+def test_encoder_layout_and_oracle_cpu():
+    from oracle import vae_oracle as V
+    from transformer_latent_diffusion_b200.vae import vae_encoder_param_layout
+
+    lay = vae_encoder_param_layout()
+    assert lay["encoder.conv_in.weight"] == (128, 3, 3, 3)
+    assert lay["encoder.down_blocks.1.resnets.0.conv_shortcut.weight"] == (256, 128, 1, 1)
+    assert "encoder.down_blocks.3.downsamplers.0.conv.weight" not in lay
+    assert lay["encoder.conv_out.weight"] == (8, 512, 3, 3) and lay["quant_conv.weight"] == (8, 8, 1, 1)
+    assert sum(math.prod(s) for s in lay.values()) == 34_163_592 + 72   # SDXL-VAE encoder + quant_conv
+    m = _small_encoder()
+    x = torch.rand(2, 3, 32, 32) * 2 - 1
+    (post,) = m.encode(x)
+    mean, logvar = V.encode_moments({k: v.detach() for k, v in m.state_dict().items()}, x)
+    assert post.mean.shape == (2, 4, 4, 4)
+    assert rel_fro(post.mean, mean) < 1e-4 and rel_fro(post.logvar, logvar) < 1e-4
+    eps = torch.randn(2, 4, 4, 4)
+    assert rel_fro(post.sample(noise=eps), V.gaussian_sample(mean, logvar, eps)) < 1e-4
+    assert torch.equal(post.mode(), post.mean)
+
+
+def test_oracle_latent_quantisers_match_reference_vectors():
+    """oracle restatement of tld/data.py:51-60 == vectors produced by the reference's own source (make_golden_quant.py)"""
+    from oracle import vae_oracle as V
+
+    d = np.load(GOLD_Q)
+    l32, l16 = torch.from_numpy(d["lat32"]), torch.from_numpy(d["lat16"])
+    assert (V.quantize_latents(l32).numpy() == d["q32"]).all()
+    assert (V.quantize_latents(l32, 5.0).numpy() == d["q32_clip5"]).all()
+    assert (V.quantize_latents(l16).numpy() == d["q16"]).all()
+    b = torch.arange(256, dtype=torch.uint8)
+    assert (V.dequantize_latents(b).numpy() == d["deq"]).all() and (V.dequantize_latents(b, 5.0).numpy() == d["deq_clip5"]).all()
+
+
+def test_data_helpers_refuse_cpu_tensors():
+    from transformer_latent_diffusion_b200 import _lib
+    from transformer_latent_diffusion_b200.data import dequantize_latents, quantize_latents
+
+    with pytest.raises(_lib.TldError):
+        quantize_latents(torch.zeros(4))
+    with pytest.raises(_lib.TldError):
+        dequantize_latents(torch.zeros(4, dtype=torch.uint8))
+
+
+@pytest.mark.gpu
+def test_latent_quantiser_kernels_bit_exact():
+    """tld_latent_quantize / tld_latent_dequantize against the reference-generated vectors, every byte"""
+    from transformer_latent_diffusion_b200.data import dequantize_latents, quantize_latents
+
+    d = np.load(GOLD_Q)
+    l32, l16 = torch.from_numpy(d["lat32"]).cuda(), torch.from_numpy(d["lat16"]).cuda()
+    assert (quantize_latents(l32).cpu().numpy() == d["q32"]).all()
+    assert (quantize_latents(l32, 5.0).cpu().numpy() == d["q32_clip5"]).all()
+    assert (quantize_latents(l16).cpu().numpy() == d["q16"]).all()
+    b = torch.arange(256, dtype=torch.uint8, device="cuda")
+    got, got5 = dequantize_latents(b), dequantize_latents(b, 5.0)
+    assert got.dtype == torch.float16
+    assert (got.cpu().numpy().view(np.uint16) == d["deq"].view(np.uint16)).all()
+    assert (got5.cpu().numpy().view(np.uint16) == d["deq_clip5"].view(np.uint16)).all()
+    # size-independent properties at a dataset-sized tensor: idempotence of quantise(dequantise(.)) and monotonicity
+    big = torch.randint(0, 256, (1 << 22,), dtype=torch.uint8, device="cuda")
+    rt = quantize_latents(dequantize_latents(big)).int()
+    assert (rt - big.int()).abs().max() <= 1   # fp16 rounding of the dequantised value may move a byte by one, never more
+    x = torch.linspace(-25, 25, 100001, device="cuda")
+    q = quantize_latents(x).int()
+    assert (q[1:] >= q[:-1]).all() and q[0] == 0 and q[-1] == 255
+
+
+@pytest.mark.gpu
+def test_encode_gpu_matches_oracle_and_roundtrip():
+    from oracle import vae_oracle as V
+    from transformer_latent_diffusion_b200.data import decode_latents, dequantize_latents, encode_image, quantize_latents
+    from transformer_latent_diffusion_b200.vae import AutoencoderKLDecoder
+
+    m = _small_encoder(block_out=(128, 128, 256, 256), seed=3)   # widths that take the fused kernels / tcgen05 convs
+    img = torch.rand(3, 3, 64, 64)
+    mean, logvar = V.encode_moments({k: v.detach() for k, v in m.state_dict().items()}, img * 2 - 1)
+    torch.backends.cudnn.allow_tf32 = False
+    (p32,) = m.cuda().encode((img * 2 - 1).cuda())
+    assert rel_fro(p32.mean, mean) < 1e-4 and rel_fro(p32.logvar, logvar) < 1e-4
+    mb = m.to(torch.bfloat16)
+    (pb,) = mb.encode((img * 2 - 1).cuda())
+    assert rel_fro(pb.mean, mean) < 8e-2
+    assert mb.own_launches > 0, "the encoder did not reach the library kernels"
+    # the data-preparation chain of tld/data.py: encode -> quantise (device) -> dequantise -> decode
+    lat = encode_image(img, mb, generator=torch.Generator(device="cuda").manual_seed(0), to_cpu=False)
+    assert lat.shape == (3, 4, 8, 8) and lat.dtype == torch.float16 and lat.is_cuda
+    q = quantize_latents(lat)
+    back = dequantize_latents(q)
+    assert q.dtype == torch.uint8 and (back.float() - lat.float().clip(-20, 20)).abs().max() <= 40.0 / 255 + 1e-2
+    dec = AutoencoderKLDecoder(block_out=(128, 128, 256, 256)).cuda().to(torch.bfloat16)
+    out = decode_latents(back, dec)
+    assert out.shape == (3, 3, 64, 64) and out.min() >= 0 and out.max() <= 1

@@ -4,6 +4,7 @@
 //   channels-last GroupNorm + separate SiLU/elementwise kernels); the 3x3 convolutions stay on cuDNN in round 1.
 // Reference call site: tld/diffusion.py:91 -> diffusers AutoencoderKL.decode (ResnetBlock2D: GroupNorm -> SiLU ->
 // conv3x3, UpSample2D: nearest 2x -> conv3x3).
+#include <cuda_fp16.h>
 #include "common.h"
 
 namespace tld {
@@ -233,6 +234,67 @@ __global__ void __launch_bounds__(256) image_grid_u8_kernel(const TIn* __restric
   out[i * 3 + 2] = v[2];
 }
 
+// ------------------------------------------------------------------------------------------------
+// uint8 latent storage of the dataset files (tld/data.py:51-60), HBM-bound byte work: 4 latents per thread.
+//   quantize:   q = trunc(((clip(x, -c, c) / c + 1) / 2) * 255)      fp32 input: fp32 arithmetic (IEEE, no contraction);
+//                                                                   fp16 input: every step rounded to fp16, as torch does
+//   dequantize: x = ((half(q) / 255) * 2 - 1) * c                    fp16 out, every step rounded to fp16
+// Bit-exact against vectors produced by the reference's own source (tests/golden/latent_quant.npz).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float h_round(float v) { return __half2float(__float2half_rn(v)); }
+
+template <bool HALF_IN>
+__global__ void __launch_bounds__(256) latent_quantize_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, long long n,
+                                                              float c) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  float v;
+  if constexpr (HALF_IN) {
+    v = __half2float(reinterpret_cast<const __half*>(in)[i]);
+    v = fminf(fmaxf(v, -c), c);
+    v = h_round(__fdiv_rn(v, c));
+    v = h_round(__fadd_rn(v, 1.0f));
+    v = h_round(__fmul_rn(v, 0.5f));
+    v = h_round(__fmul_rn(v, 255.0f));
+  } else {
+    v = reinterpret_cast<const float*>(in)[i];
+    v = fminf(fmaxf(v, -c), c);
+    v = __fdiv_rn(v, c);
+    v = __fadd_rn(v, 1.0f);
+    v = __fmul_rn(v, 0.5f);
+    v = __fmul_rn(v, 255.0f);
+  }
+  out[i] = (uint8_t)v;
+}
+
+__global__ void __launch_bounds__(256) latent_dequantize_kernel(const uint8_t* __restrict__ q, __half* __restrict__ out,
+                                                                long long n, float c) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  float v = (float)q[i];
+  v = h_round(__fdiv_rn(v, 255.0f));
+  v = h_round(__fmul_rn(v, 2.0f));
+  v = h_round(__fadd_rn(v, -1.0f));
+  out[i] = __float2half_rn(__fmul_rn(v, c));
+}
+
+int launch_latent_quantize(const void* in, int is_fp16, uint8_t* out, long long n, float clip_val, cudaStream_t st) {
+  TLD_CHECK(n >= 0 && clip_val > 0.f, "latent_quantize: bad arguments");
+  if (n == 0) return 0;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (is_fp16) latent_quantize_kernel<true><<<blocks, 256, 0, st>>>(in, out, n, clip_val);
+  else latent_quantize_kernel<false><<<blocks, 256, 0, st>>>(in, out, n, clip_val);
+  TLD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int launch_latent_dequantize(const uint8_t* q, void* out_fp16, long long n, float clip_val, cudaStream_t st) {
+  TLD_CHECK(n >= 0 && clip_val > 0.f, "latent_dequantize: bad arguments");
+  if (n == 0) return 0;
+  latent_dequantize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q, reinterpret_cast<__half*>(out_fp16), n, clip_val);
+  TLD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int launch_image_grid_u8(const void* img, int is_bf16, uint8_t* out, int B, int H, int W, int ncol, int pad, cudaStream_t st) {
   TLD_CHECK(B > 0 && H > 0 && W > 0 && ncol > 0 && pad >= 0, "image_grid_u8: bad shape");
   const int nc = ncol < B ? ncol : B, nr = (B + nc - 1) / nc;
@@ -268,6 +330,14 @@ __attribute__((visibility("default"))) int tld_vae_conv3x3(const uint16_t* x, co
   return tld::launch_conv3x3(reinterpret_cast<const tld::bf16*>(x), reinterpret_cast<const tld::bf16*>(w), bias,
                              reinterpret_cast<tld::bf16*>(out), batch, h, w_px, cin, cout,
                              reinterpret_cast<cudaStream_t>(stream));
+}
+__attribute__((visibility("default"))) int tld_latent_quantize(const void* lat, int is_fp16, uint8_t* out, long long n,
+                                                               float clip_val, void* stream) {
+  return tld::launch_latent_quantize(lat, is_fp16, out, n, clip_val, reinterpret_cast<cudaStream_t>(stream));
+}
+__attribute__((visibility("default"))) int tld_latent_dequantize(const uint8_t* q, uint16_t* out_fp16, long long n,
+                                                                 float clip_val, void* stream) {
+  return tld::launch_latent_dequantize(q, out_fp16, n, clip_val, reinterpret_cast<cudaStream_t>(stream));
 }
 __attribute__((visibility("default"))) int tld_image_grid_u8(const void* img, int is_bf16, uint8_t* out, int batch, int h,
                                                              int w, int ncol, int pad, void* stream) {

@@ -284,3 +284,124 @@ class AutoencoderKLDecoder(nn.Module):
             prev = cout
         f += 2.0 * n * block_out[0] * 3 * 9
         return f
+
+
+# =====================================================================================================================
+# Encoder half: ``vae.encode(x)[0].sample()`` as tld/data.py:35-41 calls it when the dataset's
+# latents are produced.  Same status as the decoder: the architecture follows the published diffusers AutoencoderKL
+# encoder with diffusers-compatible keys (``encoder.*``, ``quant_conv``) and PARITY IS UNPINNED; it is checked against
+# ``oracle/vae_oracle.py:encode_moments`` on random weights.  All ResNet / GroupNorm / attention stages reuse the decoder's
+# building blocks (tcgen05 implicit-GEMM 3x3 convs, fused GroupNorm+SiLU, fused residual add); the three stride-2
+# downsampling convs, conv_in (3 channels), conv_out (8 channels) and quant_conv run on library kernels.
+# =====================================================================================================================
+def vae_encoder_param_layout(latent_ch: int = LATENT_CH, block_out=BLOCK_OUT, in_ch: int = 3) -> "Dict[str, tuple]":
+    """Ordered {key: shape} of the encoder half of diffusers.AutoencoderKL (encoder + quant_conv)."""
+    lay: Dict[str, tuple] = {}
+
+    def conv(name, cout, cin, k):
+        lay[name + ".weight"] = (cout, cin, k, k)
+        lay[name + ".bias"] = (cout,)
+
+    def norm(name, c):
+        lay[name + ".weight"] = (c,)
+        lay[name + ".bias"] = (c,)
+
+    def resnet(name, cin, cout):
+        norm(name + ".norm1", cin)
+        conv(name + ".conv1", cout, cin, 3)
+        norm(name + ".norm2", cout)
+        conv(name + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(name + ".conv_shortcut", cout, cin, 1)
+
+    conv("encoder.conv_in", block_out[0], in_ch, 3)
+    prev = block_out[0]
+    for i, cout in enumerate(block_out):
+        for j in range(LAYERS_PER_BLOCK):
+            resnet(f"encoder.down_blocks.{i}.resnets.{j}", prev if j == 0 else cout, cout)
+        if i != len(block_out) - 1:
+            conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", cout, cout, 3)
+        prev = cout
+    top = block_out[-1]
+    resnet("encoder.mid_block.resnets.0", top, top)
+    a = "encoder.mid_block.attentions.0"
+    norm(a + ".group_norm", top)
+    for p in ("to_q", "to_k", "to_v", "to_out.0"):
+        lay[f"{a}.{p}.weight"] = (top, top)
+        lay[f"{a}.{p}.bias"] = (top,)
+    resnet("encoder.mid_block.resnets.1", top, top)
+    norm("encoder.conv_norm_out", top)
+    conv("encoder.conv_out", 2 * latent_ch, top, 3)
+    conv("quant_conv", 2 * latent_ch, 2 * latent_ch, 1)
+    return lay
+
+
+class DiagonalGaussian:
+    """The posterior ``encode`` returns (diffusers' DiagonalGaussianDistribution): ``mean``, ``logvar`` (clamped to
+    [-30, 20]), ``std``; ``sample(generator)`` = mean + std * N(0, 1); ``mode()`` = mean."""
+
+    def __init__(self, moments: torch.Tensor):
+        self.mean, logvar = moments.chunk(2, dim=1)
+        self.logvar = logvar.clamp(-30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+
+    def sample(self, generator=None, noise: torch.Tensor = None) -> torch.Tensor:
+        if noise is None:
+            noise = torch.randn(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        return self.mean + self.std * noise.to(self.mean.dtype)
+
+    def mode(self) -> torch.Tensor:
+        return self.mean
+
+
+class AutoencoderKLEncoder(AutoencoderKLDecoder):
+    """``encode(x) -> (DiagonalGaussian,)`` with the SDXL-VAE encoder topology; x is an RGB image in [-1, 1]
+    (tld/data.py:38-40).  Inherits the decoder's kernels-backed building blocks; only the parameter layout and the
+    forward wiring differ."""
+
+    def __init__(self, latent_ch: int = LATENT_CH, block_out: Tuple[int, ...] = BLOCK_OUT, chunk: int = 16):
+        nn.Module.__init__(self)
+        self.latent_ch, self.block_out, self.chunk = latent_ch, tuple(block_out), chunk
+        self.own_launches = 0
+        self._layout = vae_encoder_param_layout(latent_ch, block_out)
+        for key, shape in self._layout.items():
+            if key.endswith("weight") and len(shape) == 1:
+                t = torch.ones(shape)
+            elif key.endswith("bias"):
+                t = torch.zeros(shape)
+            else:
+                fan_in = int(math.prod(shape[1:]))
+                t = torch.empty(shape).uniform_(-1.0 / math.sqrt(fan_in), 1.0 / math.sqrt(fan_in))
+            _attach(self, key, t)
+
+    def _downsample(self, x, name):
+        # diffusers Downsample2D(padding=0): pad right/bottom by one pixel, 3x3 conv with stride 2
+        return F.conv2d(F.pad(x, (0, 1, 0, 1)), self._p(name + ".weight"), self._p(name + ".bias"), stride=2)
+
+    def _encode_chunk(self, x):
+        h = self._conv(x, "encoder.conv_in", 1)
+        n_down = len(self.block_out)
+        for i in range(n_down):
+            for j in range(LAYERS_PER_BLOCK):
+                h = self._resnet(h, f"encoder.down_blocks.{i}.resnets.{j}")
+            if i != n_down - 1:
+                h = self._downsample(h, f"encoder.down_blocks.{i}.downsamplers.0.conv")
+        h = self._resnet(h, "encoder.mid_block.resnets.0")
+        h = self._mid_attention(h, "encoder.mid_block.attentions.0")
+        h = self._resnet(h, "encoder.mid_block.resnets.1")
+        h = self._group_norm(h, "encoder.conv_norm_out", True)
+        h = self._conv(h, "encoder.conv_out", 1)
+        return self._conv(h, "quant_conv", 0)
+
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor, return_dict: bool = False):
+        """x [B,3,H,W] in [-1,1] -> (DiagonalGaussian over [B,4,H/8,W/8],); processed in chunks of ``self.chunk`` images."""
+        w = self._p("encoder.conv_in.weight")
+        xx = x.to(device=w.device, dtype=w.dtype)
+        if xx.is_cuda:
+            xx = xx.contiguous(memory_format=torch.channels_last)
+        moments = torch.cat([self._encode_chunk(xx[i:i + self.chunk]) for i in range(0, xx.shape[0], self.chunk)])
+        return (DiagonalGaussian(moments.to(x.dtype if x.is_floating_point() else w.dtype).contiguous()),)
+
+    def decode(self, z):  # the encoder half has no decoder weights
+        raise NotImplementedError("AutoencoderKLEncoder holds the encoder half only; use AutoencoderKLDecoder.decode")
