@@ -147,7 +147,8 @@ def test_layernorm(lib, rows, D):
 
 @pytest.mark.parametrize("impl", [1, 2, 3])
 @pytest.mark.parametrize("B,n_tok,D", [(1, 64, 128), (2, 256, 128), (3, 256, 768), (1, 1024, 256), (1, 4096, 128),
-                                       (40, 128, 768), (17, 256, 768), (2, 1024, 768)])   # > 2 tiles per persistent CTA
+                                       (40, 128, 768), (17, 256, 768), (2, 1024, 768),   # > 2 tiles per persistent CTA
+                                       (3, 384, 192), (50, 384, 320)])                   # 3 q-tiles / 3 and 5 heads: multiply-high tile split
 def test_self_attention(lib, B, n_tok, D, impl):
     if impl >= 2 and n_tok % 128:
         pytest.skip("tcgen05 attention needs n_tok % 128 == 0")
