@@ -210,6 +210,9 @@ def run_b200(args) -> None:
         import torch.distributed as dist_mod
 
         dist = dist_mod
+        # stdout carries exactly one JSON line: whatever NCCL_DEBUG the environment sets (the "NCCL version ..." banner
+        # goes to stdout by default) is sent to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     B = args.batch  # images per GPU per step (weak scaling: fixed per-GPU work)
