@@ -191,7 +191,8 @@ def test_self_attention_persistent_variants(lib, emu, qk_scale):
     assert rel_fro(x, ref) < 6e-3, _err_map(x, ref)
 
 
-@pytest.mark.parametrize("B,grid,C", [(1, 8, 512), (2, 16, 1024), (2, 16, 3072), (1, 32, 512)])
+@pytest.mark.parametrize("B,grid,C", [(1, 8, 512), (2, 16, 1024), (2, 16, 3072), (1, 32, 512), (3, 32, 128), (2, 64, 256),
+                                      (1, 64, 3072), (2, 32, 36)])
 def test_dwconv_gelu(lib, B, grid, C):
     g = torch.Generator(device="cuda").manual_seed(6)
     h = torch.randn(B, grid, grid, C, device="cuda", generator=g).bfloat16()

@@ -123,6 +123,7 @@ void set_gemm_ctas(int v);  // 0 auto, 1 single-CTA tiles, 2 CTA-pair tiles (exp
 // 2-D row-major TMA descriptor (bf16 or fp32), box = [box_rows, 128 bytes], 128B swizzle (gemm.cu)
 int make_tmap_2d(CUtensorMap* m, const void* base, bool is_f32, long long rows, long long cols, long long ld,
                  int box_rows);
+int make_tmap_tokens3d(CUtensorMap* m, const void* base, int B, int npos, int C, int box_pos);  // [B][npos][C] bf16
 
 // ---------------------------------------------------------------- attention.cu / attention_tc.cu
 // x[T,D] fp32 += softmax(q k^T / 8) v per (sample, head); qkv bf16 [T,3D] (q | k | v), head_dim 64

@@ -62,6 +62,21 @@ static int make_tmap_nhwc(CUtensorMap* m, const void* base, int B, int H, int W,
   return 0;
 }
 
+// 3-D view [B][positions][C] of a token-major bf16 activation: box = [64 ch, box_pos, 1], 128B swizzle.  Positions outside
+// [0, npos) of the SAME image are zero-filled (a 2-D [B*npos, C] view would read the neighbouring image instead).
+int make_tmap_tokens3d(CUtensorMap* m, const void* base, int B, int npos, int C, int box_pos) {
+  if (resolve_encode()) return fail("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)npos, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)npos * C * 2};
+  cuuint32_t box[3] = {64u, (cuuint32_t)box_pos, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(3d) failed, CUresult=" + std::to_string((int)r));
+  return 0;
+}
+
 template <int BN, int EPI, int CTAS>
 static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
                     const GemmEpi& ep, cudaStream_t st) {

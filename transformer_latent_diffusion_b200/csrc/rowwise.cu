@@ -621,6 +621,104 @@ __global__ void __launch_bounds__(256) dwconv_gelu_g16_kernel(const __grid_const
   }
 }
 
+// Larger token grids (32x32: 512-px model, 64x64: 1024-px model): the same shared-memory scheme on ROW TILES.  One CTA =
+// one image x 64 channels x RT output rows; the RT+2 input rows (one halo row above and below) arrive as TMA boxes of two
+// grid rows each from a 3-D [image][position][channel] view, so rows outside the image are zero-filled by the TMA unit
+// (= the conv's zero padding, no border flags).  A warp produces two output rows over a segment of G/XS columns, sliding
+// along x with a 4-row x 3-column fp32 window; lane = channel pair (conflict-free 128-byte LDS rows, FFMA2 arithmetic).
+template <int G, int RT, int XS>
+__global__ void __launch_bounds__(32 * (RT / 2) * XS) dwconv_gelu_rows_kernel(const __grid_constant__ CUtensorMap tmap_h,
+                                                                            const float* __restrict__ w9,
+                                                                            const float* __restrict__ bias,
+                                                                            bf16* __restrict__ g, int C) {
+  static_assert(RT % 2 == 0 && G % RT == 0 && G % XS == 0 && (2 * G) % 8 == 0 && 2 * G <= 256, "bad row tiling");
+  constexpr int TROWS = RT + 2, XW = G / XS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tile = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tile + TROWS * G * 128);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = blockIdx.x * 64;
+  const int tiles_per_img = G / RT;
+  const int b = blockIdx.y / tiles_per_img, ty0 = (blockIdx.y % tiles_per_img) * RT;   // first output row of this CTA
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    pdl_wait();  // h is the previous kernel's output
+    mbar_expect_tx(bar, TROWS * G * 128);
+#pragma unroll
+    for (int r2 = 0; r2 < TROWS / 2; ++r2)   // box = two grid rows; the first starts one row above the tile (may be row -1)
+      tma_load_3d(tile + r2 * 2 * G * 128, &tmap_h, bar, c0, (ty0 - 1 + 2 * r2) * G, b);
+  }
+  const int ch = c0 + 2 * lane;
+  float2 w[9];
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp) w[tp] = __ldg(reinterpret_cast<const float2*>(w9 + (size_t)tp * C + ch));
+  const float2 bs = __ldg(reinterpret_cast<const float2*>(bias + ch));
+  __syncthreads();  // barrier init visible before anyone polls it
+  pdl_wait();
+  mbar_wait(bar, 0);
+
+  const int wr = warp / XS, ws = warp % XS;      // row pair / column segment of this warp
+  const int y0 = 2 * wr, x0 = ws * XW;           // output rows ty0+y0, ty0+y0+1 = tile rows y0+1, y0+2; inputs y0 .. y0+3
+  const uint32_t rows = smem_u32(tile) + y0 * G * 128;
+  const int lane_chunk = lane >> 2, lane_off = (lane & 3) * 4;
+  auto ldcol = [&](float2 (&dst)[4], int x) {
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int tp = rr * G + x;   // (y0 * G) is a multiple of 8, so the swizzle phase of the row is tp & 7 == x & 7
+      uint32_t v;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(rows + tp * 128 + ((lane_chunk ^ (x & 7)) << 4) + lane_off));
+      dst[rr] = unpack_bf16x2(v);
+    }
+  };
+  float2 win[3][4];
+  // window columns x0-1, x0, x0+1 in slots 2, 0, 1 (slot of column x = (x - x0) mod 3, column x0-1 takes slot 2)
+  if (x0 > 0) {
+    ldcol(win[2], x0 - 1);
+  } else {
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) win[2][rr] = make_float2(0.f, 0.f);
+  }
+  ldcol(win[0], x0);
+  ldcol(win[1], x0 + 1);
+  bf16* out = g + ((size_t)b * G * G + (size_t)(ty0 + y0) * G + x0) * C + ch;
+#pragma unroll
+  for (int xi = 0; xi < XW; ++xi) {
+    float2 a0 = bs, a1 = bs;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        a0 = ffma2(w[dy * 3 + dx], win[(xi + dx + 2) % 3][dy], a0);
+        a1 = ffma2(w[dy * 3 + dx], win[(xi + dx + 2) % 3][dy + 1], a1);
+      }
+    const float2 g0 = gelu2(a0), g1 = gelu2(a1);
+    *reinterpret_cast<uint32_t*>(out + (size_t)xi * C) = pack_bf16x2_dev(g0.x, g0.y);
+    *reinterpret_cast<uint32_t*>(out + (size_t)(G + xi) * C) = pack_bf16x2_dev(g1.x, g1.y);
+    if (x0 + xi + 2 < G) {
+      ldcol(win[(xi + 2) % 3], x0 + xi + 2);
+    } else {
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) win[(xi + 2) % 3][rr] = make_float2(0.f, 0.f);
+    }
+  }
+}
+
+template <int G, int RT, int XS>
+static int launch_dwconv_rows(const bf16* h, const float* w9, const float* bias, bf16* g, int B, int C, cudaStream_t st) {
+  constexpr int smem = 1024 + (RT + 2) * G * 128 + 64;
+  auto kern = dwconv_gelu_rows_kernel<G, RT, XS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TLD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  CUtensorMap th;
+  if (make_tmap_tokens3d(&th, h, B, G * G, C, 2 * G)) return 1;
+  return launch_pdl(kern, dim3(C / 64, B * (G / RT)), dim3(32 * (RT / 2) * XS), smem, st, th, w9, bias, g, C);
+}
+
 int launch_dwconv_gelu(const bf16* h, const float* w9, const float* bias, bf16* g, int B, int grid, int C,
                        cudaStream_t st) {
   TLD_CHECK(C % 4 == 0, "dwconv: channel count must be a multiple of 4");
@@ -634,6 +732,10 @@ int launch_dwconv_gelu(const bf16* h, const float* w9, const float* bias, bf16* 
     if (make_tmap_2d(&th, h, false, (long long)B * 256, C, C, 256)) return 1;
     return launch_pdl(dwconv_gelu_g16_kernel<0>, dim3(C / 64, B), dim3(256), smem, st, th, w9, bias, g, C,
                       (const bf16*)nullptr);
+  }
+  if (C % 64 == 0 && (long long)B * grid <= 65535) {
+    if (grid == 32) return launch_dwconv_rows<32, 16, 1>(h, w9, bias, g, B, C, st);   // 18 rows x 32 = 72 KB, 8 warps
+    if (grid == 64) return launch_dwconv_rows<64, 8, 2>(h, w9, bias, g, B, C, st);    // 10 rows x 64 = 80 KB, 8 warps
   }
   switch (grid) {
     case 8: dwconv_gelu_grid_kernel<8><<<blocks, 256, 0, st>>>(h, w9, bias, g, B, C); break;
