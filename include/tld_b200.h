@@ -145,6 +145,14 @@ TLD_API int tld_train_forward(tld_denoiser* h, const float* x, const float* nois
                               int batch, void* stream);
 TLD_API int tld_train_backward(tld_denoiser* h, const float* d_pred, int batch, void* stream);
 TLD_API int tld_train_get_grad(tld_denoiser* h, const char* key, float* dst, int64_t numel, void* stream);
+/* Data-parallel training (tld/train.py:109,169: accelerate/DDP all-reduces gradient buckets while the backward is still
+ * running).  All gradients live in ONE device arena; tld_train_grad_layout returns it as n_layers + 2 ranges
+ * (out[2i] = element offset, out[2i+1] = elements): range l < n_layers = decoder block l (without kv_linear), range n_layers =
+ * all kv_linear weights, range n_layers + 1 = everything else.  tld_train_wait_grad makes `stream` wait (device-side only)
+ * until range `segment` of the backward enqueued last is final (segment >= n_layers: the whole backward), so the caller can
+ * all-reduce block l in place on a side stream while blocks l-1..0 are still being differentiated. */
+TLD_API int tld_train_grad_layout(tld_denoiser* h, float** arena, int64_t* total, int64_t* out, int n_segments);
+TLD_API int tld_train_wait_grad(tld_denoiser* h, int segment, void* stream);
 
 /* ---- backward-pass ops of the training step (autograd through tld/transformer_blocks.py:135-139, driven by
  * tld/train.py:160-170), exported for the parity tests (tests/test_backward_gpu.py) ------------------------------

@@ -73,8 +73,21 @@ def _grad_worker(rank, world, port, out):
     for i, p in enumerate(m.parameters()):
         p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
     allreduce_gradients(m)
+    # a model whose backward already averaged its gradients (overlapped NCCL path, train.py:_overlapped_allreduce) is
+    # left alone exactly once, and without NCCL the overlapped path declines so the plain all-reduce above still runs
+    from transformer_latent_diffusion_b200.train import _overlapped_allreduce
+
+    m2 = torch.nn.Linear(2, 2)
+    for p in m2.parameters():
+        p.grad = torch.full_like(p, float(rank + 1))
+    m2._tld_grads_allreduced = True
+    allreduce_gradients(m2)
+    skipped = all(torch.equal(p.grad, torch.full_like(p, float(rank + 1))) for p in m2.parameters())
+    allreduce_gradients(m2)   # flag consumed: now it averages
+    averaged = all(torch.allclose(p.grad, torch.full_like(p, 1.5)) for p in m2.parameters())
+    declined = _overlapped_allreduce(m2, None, torch.device("cpu")) is False
     if rank == 0:
-        torch.save([p.grad.clone() for p in m.parameters()], out)
+        torch.save([p.grad.clone() for p in m.parameters()] + [torch.tensor([skipped, averaged, declined])], out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -87,6 +100,7 @@ def test_allreduce_gradients_gloo_world2(tmp_path):
     s.close()
     out = str(tmp_path / "g.pt")
     mp.spawn(_grad_worker, args=(2, port, out), nprocs=2, join=True)
-    grads = torch.load(out)
+    *grads, flags = torch.load(out)
+    assert flags.all(), flags
     for i, g in enumerate(grads):
         assert torch.allclose(g, torch.full_like(g, 1.5 * (i + 1)))  # mean of (1, 2) * (i + 1)

@@ -8,6 +8,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--no-overlap", action="store_true", help="all-reduce after the backward instead of overlapped with it")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -18,6 +19,7 @@ def main():
     from transformer_latent_diffusion_b200.train import train_step, update_ema, noise_batch
     torch.manual_seed(0)
     m = Denoiser(32, 256, 2, 768, 0, 12).cuda().train()
+    m.overlap_grad_allreduce = not a.no_overlap
     ema = copy.deepcopy(m)
     opt = torch.optim.Adam(m.parameters(), lr=3e-4, fused=True)
     B = a.batch
@@ -43,7 +45,9 @@ def main():
     ms = e0.elapsed_time(e1) / a.steps
     if int(os.environ.get("RANK", "0")) == 0:
         fl = 3 * 46.163e9 * B
-        print(f"train step B={B}/GPU x{world}: {ms:.2f} ms  loss {float(l):.4f}  -> {B * world / ms * 1e3:.0f} samples/s, {fl / ms / 1e9:.0f} TFLOP/s per GPU (3x fwd FLOPs)")
+        chk = sum(float(p.detach().double().abs().sum()) for p in m.parameters())
+        mode = "" if world == 1 else (" all-reduce after backward" if a.no_overlap else " all-reduce overlapped")
+        print(f"train step B={B}/GPU x{world}{mode}: {ms:.2f} ms  loss {float(l):.4f}  -> {B * world / ms * 1e3:.0f} samples/s, {fl / ms / 1e9:.0f} TFLOP/s per GPU (3x fwd FLOPs)  param checksum {chk:.6f}")
     if world > 1:
         dist.destroy_process_group()
 main()

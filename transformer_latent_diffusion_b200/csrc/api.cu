@@ -312,6 +312,8 @@ void tld_denoiser_destroy(tld_denoiser* h) {
   void* extra[] = {h->ycond, h->kv, h->tlevels, h->cond_scratch, h->x_t, h->x0_prev, h->x0_out, h->step_table};
   for (void* p : extra)
     if (p) cudaFree(p);
+  for (cudaEvent_t e : h->ev_grad)
+    if (e) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   cudaEvent_t evs[] = {h->ev_in, h->ev_out, h->ev_t0, h->ev_t1};
   for (cudaEvent_t e : evs)

@@ -86,6 +86,7 @@ struct tld_denoiser {
   std::map<std::string, std::pair<float*, long long>> grads;  // reference-layout fp32 gradient of every parameter
   float* grad_arena = nullptr;
   long long grad_elems = 0;
+  std::vector<cudaEvent_t> ev_grad;  // [L+1]: gradients of layer l complete (l < L) / whole backward complete (index L)
   // scratch (sized with train_batch)
   float *t_dx = nullptr, *t_dxn = nullptr, *t_xfinal = nullptr;
   bf16 *t_a = nullptr, *t_aT = nullptr, *t_big = nullptr, *t_bigT = nullptr, *t_big2 = nullptr, *t_xnT = nullptr, *t_q = nullptr;

@@ -7,6 +7,9 @@
 //   wgrad  dW[N,K]  = dY^T[N,T] * X[T,K]        -> launch_gemm_mn(A = dY, B = X): MN-major operands, no transposes
 // Everything else is the HBM-bound kernels of backward.cu / attention_bwd.cu plus a few tiny fp32 products for the
 // 16-wide patch/out projections and the B-row conditioning path.  The residual-stream gradient stays fp32.
+#include <algorithm>
+#include <cstdlib>
+
 #include "gemm_tcgen05.cuh"
 #include "handle.h"
 
@@ -183,7 +186,10 @@ static int ensure_train(tld_denoiser* h, int B) {
     long long total = 0;
     for (auto& kv : h->slots) total += kv.second.numel;
     TLD_CUDA_OK(cudaMalloc(&h->grad_arena, (size_t)total * sizeof(float)));
+    TLD_CUDA_OK(cudaMemset(h->grad_arena, 0, (size_t)total * sizeof(float)));   // buffer slots are never written
     h->grad_elems = total;
+    h->ev_grad.resize(L + 1);
+    for (auto& e : h->ev_grad) TLD_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     // the L kv_linear gradients must be contiguous (one wgrad GEMM over the concatenated [L*2D, D] weight)
     long long off = 0;
     for (int l = 0; l < L; ++l) {
@@ -364,6 +370,7 @@ TLD_API int tld_train_backward(tld_denoiser* h, const float* d_pred, int batch, 
       return 1;                                                                                     // dqkv^T xn
     if (launch_gemm(EPI_F32, h->t_big, 3 * D, wt.wqkvT, 3 * D, T, D, 3 * D, h->t_dxn, D, nullptr, nullptr, st)) return 1;
     if (launch_layernorm_bwd(h->t_dxn, t.xs0, ly.ln1w, h->t_dx, G(h, b + "norm1.weight"), G(h, b + "norm1.bias"), T, D, st)) return 1;
+    TLD_CUDA_OK(cudaEventRecord(h->ev_grad[l], st));   // this layer's gradients (all but kv_linear) are final
   }
 
   // ---- patch embedding (denoiser.py:34-45,75-77): tokens = LN_D(W3 LN_pd(conv(u)) + b3) + pos
@@ -407,6 +414,7 @@ TLD_API int tld_train_backward(tld_denoiser* h, const float* d_pred, int batch, 
   if (small_gemm(c_da1, 1, D, h->t_cond_emb, E, 1, G(h, "fourier_feats.1.weight"), D, E, B, st)) return 1;
   // the frequency buffer is not a parameter
   TLD_CUDA_OK(cudaMemsetAsync(G(h, "fourier_feats.0.angular_speeds"), 0, sizeof(float) * (size_t)(E / 2), st));
+  TLD_CUDA_OK(cudaEventRecord(h->ev_grad[L], st));
   return 0;
 }
 
@@ -418,6 +426,60 @@ TLD_API int tld_train_get_grad(tld_denoiser* h, const char* key, float* dst, int
   TLD_CHECK(numel == it->second.second, std::string("tld_train_get_grad: size mismatch for ") + key);
   TLD_CUDA_OK(cudaMemcpyAsync(dst, it->second.first, sizeof(float) * (size_t)numel, cudaMemcpyDeviceToDevice,
                               reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// ---- data-parallel support: the gradient arena as ranges that become final at known points of the backward, so that the
+// caller's all-reduce of layer l can run while layers l-1 .. 0 are still being differentiated (tld/train.py:169:
+// accelerator.backward = DDP's bucketed, overlapped all-reduce).
+//   segment l in [0, L): every gradient of decoder block l except its kv_linear weight;  segment L: the concatenated kv_linear
+//   gradients of all blocks;  segment L+1: everything else (patch embedding, positions, out-projection, conditioning MLP).
+// out[2*i] = element offset into the arena, out[2*i+1] = elements.  *arena receives the device pointer (fp32).
+TLD_API int tld_train_grad_layout(tld_denoiser* h, float** arena, int64_t* total, int64_t* out, int n_segments) {
+  TLD_CHECK(h && arena && total && out, "tld_train_grad_layout: null argument");
+  TLD_CHECK(h->grad_arena != nullptr, "tld_train_grad_layout: call tld_train_forward first");
+  const int L = h->L;
+  TLD_CHECK(n_segments == L + 2, "tld_train_grad_layout: n_segments must be n_layers + 2");
+  *arena = h->grad_arena;
+  *total = h->grad_elems;
+  const long long kv_elems = 2LL * h->D * h->D * L;
+  long long tail_lo = h->grad_elems, tail_sum = 0;
+  std::vector<long long> lo(L, h->grad_elems), hi(L, 0), sum(L, 0);
+  const std::string pre = "denoiser_trans_block.decoder_blocks.";
+  for (auto& kv : h->grads) {
+    const long long off = kv.second.first - h->grad_arena, n = kv.second.second;
+    if (off < kv_elems) continue;  // the kv block
+    if (kv.first.compare(0, pre.size(), pre) == 0) {
+      const int l = std::atoi(kv.first.c_str() + pre.size());
+      TLD_CHECK(l >= 0 && l < L, "tld_train_grad_layout: bad layer index in key");
+      lo[l] = std::min(lo[l], off);
+      hi[l] = std::max(hi[l], off + n);
+      sum[l] += n;
+    } else {
+      tail_lo = std::min(tail_lo, off);
+      tail_sum += n;
+    }
+  }
+  for (int l = 0; l < L; ++l) {
+    TLD_CHECK(hi[l] - lo[l] == sum[l], "tld_train_grad_layout: a layer's gradients are not contiguous");
+    out[2 * l] = lo[l];
+    out[2 * l + 1] = sum[l];
+  }
+  out[2 * L] = 0;
+  out[2 * L + 1] = kv_elems;
+  TLD_CHECK(tail_lo + tail_sum == h->grad_elems, "tld_train_grad_layout: tail gradients are not contiguous");
+  out[2 * L + 2] = tail_lo;
+  out[2 * L + 3] = tail_sum;
+  return 0;
+}
+
+// make `stream` wait until segment `segment` of the running backward is final (segment < n_layers: that layer; otherwise the
+// whole backward).  Pure stream ordering, the host does not block.
+TLD_API int tld_train_wait_grad(tld_denoiser* h, int segment, void* stream) {
+  TLD_CHECK(h && !h->ev_grad.empty(), "tld_train_wait_grad: no backward has been recorded");
+  const int L = h->L;
+  const int idx = (segment >= 0 && segment < L) ? segment : L;
+  TLD_CUDA_OK(cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(stream), h->ev_grad[idx], 0));
   return 0;
 }
 

@@ -53,12 +53,56 @@ class _DenoiserFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             st = _lib.current_stream_ptr(dev)
             _lib.check(lib.tld_train_backward(ctx.handle, _lib.ptr(g), ctx.batch, st), "tld_train_backward")
+            ctx.module._tld_grads_allreduced = _overlapped_allreduce(ctx.module, ctx.handle, dev)
             grads = []
             for key, (shape, dtype) in zip(ctx.keys, ctx.meta):
                 t = torch.empty(shape, device=dev, dtype=torch.float32)
                 _lib.check(lib.tld_train_get_grad(ctx.handle, key.encode(), _lib.ptr(t), t.numel(), st), f"get_grad({key})")
                 grads.append(t if dtype == torch.float32 else t.to(dtype))
         return (None, None, None, None, *grads)
+
+
+class _DeviceArray:
+    """zero-copy view of a device buffer for ``torch.as_tensor`` (CUDA array interface v2)"""
+
+    def __init__(self, ptr: int, numel: int):
+        self.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def _overlapped_allreduce(module, handle, dev) -> bool:
+    """Data-parallel gradient averaging overlapped with the backward (what DDP does inside ``accelerator.backward``,
+    tld/train.py:109,169).  ``tld_train_backward`` has only been ENQUEUED at this point; every decoder block's gradients
+    form one contiguous range of the library's gradient arena and become final at a recorded event, so a side stream
+    waits for block l's event and all-reduces that range in place (NCCL, average) while the compute stream is still
+    differentiating blocks l-1 .. 0.  Returns False (nothing done) without an NCCL process group of more than one rank."""
+    import ctypes as C
+
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and dist.get_backend() == "nccl"):
+        return False
+    if not getattr(module, "overlap_grad_allreduce", True):
+        return False
+    lib = _lib.load()
+    L = module.n_layers
+    arena, total = C.c_void_p(), C.c_int64()
+    seg = (C.c_int64 * (2 * (L + 2)))()
+    _lib.check(lib.tld_train_grad_layout(handle, C.byref(arena), C.byref(total), seg, L + 2), "tld_train_grad_layout")
+    cache = module.__dict__.setdefault("_tld_ddp", {})
+    if cache.get("ptr") != arena.value:
+        cache["ptr"] = arena.value
+        cache["view"] = torch.as_tensor(_DeviceArray(arena.value, total.value), device=dev)
+        cache["stream"] = torch.cuda.Stream(device=dev)
+    view, side = cache["view"], cache["stream"]
+    with torch.cuda.stream(side):
+        for l in range(L - 1, -1, -1):   # the backward finishes the blocks in this order
+            _lib.check(lib.tld_train_wait_grad(handle, l, side.cuda_stream), "tld_train_wait_grad")
+            dist.all_reduce(view[seg[2 * l]: seg[2 * l] + seg[2 * l + 1]], op=dist.ReduceOp.AVG)
+        _lib.check(lib.tld_train_wait_grad(handle, L, side.cuda_stream), "tld_train_wait_grad")
+        for i in (L, L + 1):             # all kv_linear weights; embedding / conditioning / out-projection
+            dist.all_reduce(view[seg[2 * i]: seg[2 * i] + seg[2 * i + 1]], op=dist.ReduceOp.AVG)
+    torch.cuda.current_stream(dev).wait_stream(side)   # the per-parameter copies below read averaged gradients
+    return True
 
 
 def denoiser_autograd_forward(module, x: Tensor, noise_level: Tensor, label: Tensor) -> Tensor:
@@ -118,6 +162,9 @@ def allreduce_gradients(model: nn.Module) -> None:
     import torch.distributed as dist
 
     if not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    if getattr(model, "_tld_grads_allreduced", False):   # already averaged, overlapped with the backward
+        model._tld_grads_allreduced = False
         return
     grads = [p.grad for p in model.parameters() if p.grad is not None]
     flat = torch._utils._flatten_dense_tensors(grads)
