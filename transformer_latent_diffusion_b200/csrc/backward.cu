@@ -382,6 +382,19 @@ int launch_dwconv_gelu_bwd(const bf16* hid, const bf16* dg, const float* w9, con
     dwconv_bwd_kernel<<<blocks, 256, 0, st>>>(du_tmp, nullptr, w9, bias, dhid, B, G, C, 1);
     TLD_CUDA_OK(cudaGetLastError());
   }
+  if (G == 16 && C % 64 == 0 && B <= 65535) {
+    // tap / bias gradients with the tile kernel too: one [10][C] partial per image, then the fixed-order sum over images
+    const size_t need = (size_t)B * 10 * C;
+    if (need > g_dw_partial_cap) {
+      if (g_dw_partial) cudaFree(g_dw_partial);
+      TLD_CUDA_OK(cudaMalloc(&g_dw_partial, need * sizeof(float)));
+      g_dw_partial_cap = need;
+    }
+    if (launch_dwconv_g16_bwd(hid, du_tmp, w9, bias, reinterpret_cast<bf16*>(g_dw_partial), B, C, 3, st)) return 1;
+    dwconv_bwd_dw_reduce_kernel<<<(10 * C + 255) / 256, 256, 0, st>>>(g_dw_partial, dw9, db, B, C);
+    TLD_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   const long long total = (long long)B * G * G;
   int nchunk = (int)((total + 31) / 32);   // >= 32 positions per chunk, at most 256 chunks (12 x 256 CTAs at C = 3072)
   if (nchunk > 256) nchunk = 256;

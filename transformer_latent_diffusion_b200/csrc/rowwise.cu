@@ -533,6 +533,8 @@ __global__ void __launch_bounds__(256) dwconv_gelu_grid_kernel(const bf16* __res
 // MODE 0: g = gelu(conv(h) + b)                         (forward)
 // MODE 1: out = second * gelu'(conv(h) + b)              (backward A: du = dg * gelu'(u), u recomputed)
 // MODE 2: out = conv^T(in): flipped taps, no bias        (backward B: dh = dwconv^T(du))
+// MODE 3: tap / bias gradients of this image:  partial[b][tap][c] = sum_{y,x} du[y,x,c] h[y+dy-1, x+dx-1, c],
+//         partial[b][9][c] = sum du   (tile = h, second = du, g reinterpreted as the fp32 partial buffer [B][10][C])
 template <int MODE>
 __global__ void __launch_bounds__(256) dwconv_gelu_g16_kernel(const __grid_constant__ CUtensorMap tmap_h,
                                                               const float* __restrict__ w9,
@@ -557,8 +559,9 @@ __global__ void __launch_bounds__(256) dwconv_gelu_g16_kernel(const __grid_const
   float2 w[9];
 #pragma unroll
   for (int tp = 0; tp < 9; ++tp)
-    w[tp] = __ldg(reinterpret_cast<const float2*>(w9 + (size_t)(MODE == 2 ? 8 - tp : tp) * C + ch));
-  const float2 bs = MODE == 2 ? make_float2(0.f, 0.f) : __ldg(reinterpret_cast<const float2*>(bias + ch));
+    w[tp] = MODE == 3 ? make_float2(0.f, 0.f)
+                      : __ldg(reinterpret_cast<const float2*>(w9 + (size_t)(MODE == 2 ? 8 - tp : tp) * C + ch));
+  const float2 bs = MODE >= 2 ? make_float2(0.f, 0.f) : __ldg(reinterpret_cast<const float2*>(bias + ch));
   __syncthreads();  // barrier init visible before anyone polls it
   pdl_wait();       // every thread: the output buffer may still be read by an earlier kernel
   mbar_wait(bar, 0);
@@ -586,6 +589,46 @@ __global__ void __launch_bounds__(256) dwconv_gelu_g16_kernel(const __grid_const
   ldcol(win[0], 0);
   ldcol(win[1], 1);
   bf16* out = g + ((size_t)b * G * G + (size_t)y0 * G) * C + ch;
+  if constexpr (MODE == 3) {
+    // weight-gradient mode: the same sliding window, but the products are accumulated per tap instead of per position
+    const bf16* du = second + ((size_t)b * G * G + (size_t)y0 * G) * C + ch;
+    float2 acc[9], accb = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int x = 0; x < G; ++x) {
+      const float2 d0 = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(du + (size_t)x * C)));
+      const float2 d1 = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(du + (size_t)(G + x) * C)));
+      accb = fadd2(accb, fadd2(d0, d1));
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          acc[dy * 3 + dx] = ffma2(d0, win[(x + dx + 2) % 3][dy], acc[dy * 3 + dx]);
+          acc[dy * 3 + dx] = ffma2(d1, win[(x + dx + 2) % 3][dy + 1], acc[dy * 3 + dx]);
+        }
+      if (x + 2 < G) {
+        ldcol(win[(x + 2) % 3], x + 2);
+      } else {
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) win[(x + 2) % 3][rr] = make_float2(0.f, 0.f);
+      }
+    }
+    // the 8 warps (row pairs) of the CTA -> one [10][64] block of this image's partial sums (fixed order: deterministic)
+    float* red = reinterpret_cast<float*>(tile + G * G * 128 + 64);   // [8][10][64] fp32 behind the tile and its barrier
+#pragma unroll
+    for (int t = 0; t < 9; ++t) *reinterpret_cast<float2*>(red + (warp * 10 + t) * 64 + 2 * lane) = acc[t];
+    *reinterpret_cast<float2*>(red + (warp * 10 + 9) * 64 + 2 * lane) = accb;
+    __syncthreads();
+    float* partial = reinterpret_cast<float*>(g);
+    for (int i = threadIdx.x; i < 10 * 64; i += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int wq = 0; wq < 8; ++wq) t += red[wq * 640 + i];
+      partial[((size_t)b * 10 + i / 64) * C + c0 + (i & 63)] = t;
+    }
+    return;
+  }
 #pragma unroll
   for (int x = 0; x < G; ++x) {
     float2 a0 = bs, a1 = bs;
@@ -751,10 +794,19 @@ int launch_dwconv_gelu(const bf16* h, const float* w9, const float* bias, bf16* 
 // backward passes A and B of the MLP middle on the 16x16 grid (same tile kernel, other point-wise tail)
 int launch_dwconv_g16_bwd(const bf16* in, const bf16* second, const float* w9, const float* bias, bf16* out, int B, int C,
                           int mode, cudaStream_t st) {
-  TLD_CHECK(C % 64 == 0 && B <= 65535 && (mode == 1 || mode == 2), "dwconv_g16_bwd: bad arguments");
+  TLD_CHECK(C % 64 == 0 && B <= 65535 && mode >= 1 && mode <= 3, "dwconv_g16_bwd: bad arguments");
   constexpr int smem = 1024 + 16 * 16 * 128 + 64;
   CUtensorMap th;
   if (make_tmap_2d(&th, in, false, (long long)B * 256, C, C, 256)) return 1;
+  if (mode == 3) {  // out = fp32 partial sums [B][10][C]; extra [8][10][64] fp32 reduction buffer behind the tile
+    constexpr int smem3 = smem + 8 * 10 * 64 * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+      TLD_CUDA_OK(cudaFuncSetAttribute(dwconv_gelu_g16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+      attr_set = true;
+    }
+    return launch_pdl(dwconv_gelu_g16_kernel<3>, dim3(C / 64, B), dim3(256), smem3, st, th, w9, bias, out, C, second);
+  }
   if (mode == 1)
     return launch_pdl(dwconv_gelu_g16_kernel<1>, dim3(C / 64, B), dim3(256), smem, st, th, w9, bias, out, C, second);
   return launch_pdl(dwconv_gelu_g16_kernel<2>, dim3(C / 64, B), dim3(256), smem, st, th, w9, bias, out, C,
