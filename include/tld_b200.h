@@ -153,6 +153,8 @@ TLD_API int tld_train_get_grad(tld_denoiser* h, const char* key, float* dst, int
  * all-reduce block l in place on a side stream while blocks l-1..0 are still being differentiated. */
 TLD_API int tld_train_grad_layout(tld_denoiser* h, float** arena, int64_t* total, int64_t* out, int n_segments);
 TLD_API int tld_train_wait_grad(tld_denoiser* h, int segment, void* stream);
+/* element offset / size of the gradient of `key` inside that arena (lets the caller snapshot all gradients with one copy) */
+TLD_API int tld_train_grad_offset(tld_denoiser* h, const char* key, int64_t* offset, int64_t* numel);
 
 /* ---- backward-pass ops of the training step (autograd through tld/transformer_blocks.py:135-139, driven by
  * tld/train.py:160-170), exported for the parity tests (tests/test_backward_gpu.py) ------------------------------

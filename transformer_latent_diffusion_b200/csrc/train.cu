@@ -473,6 +473,16 @@ TLD_API int tld_train_grad_layout(tld_denoiser* h, float** arena, int64_t* total
   return 0;
 }
 
+// element offset / size of one parameter's gradient inside the arena (reference state_dict key and layout)
+TLD_API int tld_train_grad_offset(tld_denoiser* h, const char* key, int64_t* offset, int64_t* numel) {
+  TLD_CHECK(h && key && offset && numel, "tld_train_grad_offset: null argument");
+  auto it = h->grads.find(key);
+  if (it == h->grads.end()) return fail(std::string("tld_train_grad_offset: unknown key ") + key);
+  *offset = it->second.first - h->grad_arena;
+  *numel = it->second.second;
+  return 0;
+}
+
 // make `stream` wait until segment `segment` of the running backward is final (segment < n_layers: that layer; otherwise the
 // whole backward).  Pure stream ordering, the host does not block.
 TLD_API int tld_train_wait_grad(tld_denoiser* h, int segment, void* stream) {

@@ -17,6 +17,7 @@
 from __future__ import annotations
 
 import copy
+import weakref
 from dataclasses import asdict
 from typing import Optional
 
@@ -54,12 +55,18 @@ class _DenoiserFn(torch.autograd.Function):
             st = _lib.current_stream_ptr(dev)
             _lib.check(lib.tld_train_backward(ctx.handle, _lib.ptr(g), ctx.batch, st), "tld_train_backward")
             ctx.module._tld_grads_allreduced = _overlapped_allreduce(ctx.module, ctx.handle, dev)
+            # ONE device copy snapshots the whole gradient arena (fresh storage per backward, so gradients that the caller
+            # keeps or accumulates never alias the library's buffers); each parameter gets a view of the snapshot
+            view, offsets = _grad_arena(ctx.module, ctx.handle, dev, ctx.keys)
+            snap = view.clone()
             grads = []
-            for key, (shape, dtype) in zip(ctx.keys, ctx.meta):
-                t = torch.empty(shape, device=dev, dtype=torch.float32)
-                _lib.check(lib.tld_train_get_grad(ctx.handle, key.encode(), _lib.ptr(t), t.numel(), st), f"get_grad({key})")
+            for (off, n), (shape, dtype) in zip(offsets, ctx.meta):
+                t = snap[off:off + n].view(shape)
                 grads.append(t if dtype == torch.float32 else t.to(dtype))
         return (None, None, None, None, *grads)
+
+
+_ARENA_CACHE = weakref.WeakKeyDictionary()   # module -> {arena pointer, tensor view, segment table, side stream}
 
 
 class _DeviceArray:
@@ -67,6 +74,31 @@ class _DeviceArray:
 
     def __init__(self, ptr: int, numel: int):
         self.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def _grad_arena(module, handle, dev, keys=None):
+    """(fp32 tensor view of the library's gradient arena, [(offset, numel) per key]) - cached per module / arena"""
+    import ctypes as C
+
+    lib = _lib.load()
+    L = module.n_layers
+    arena, total = C.c_void_p(), C.c_int64()
+    seg = (C.c_int64 * (2 * (L + 2)))()
+    _lib.check(lib.tld_train_grad_layout(handle, C.byref(arena), C.byref(total), seg, L + 2), "tld_train_grad_layout")
+    cache = _ARENA_CACHE.setdefault(module, {})   # outside the module: copy.deepcopy(model) must not drag views/streams along
+    if cache.get("ptr") != arena.value:
+        cache.clear()
+        cache["ptr"] = arena.value
+        cache["view"] = torch.as_tensor(_DeviceArray(arena.value, total.value), device=dev)
+        cache["segments"] = [(int(seg[2 * i]), int(seg[2 * i + 1])) for i in range(L + 2)]
+    if keys is not None and cache.get("keys") != keys:
+        offs = []
+        for key in keys:
+            off, n = C.c_int64(), C.c_int64()
+            _lib.check(lib.tld_train_grad_offset(handle, key.encode(), C.byref(off), C.byref(n)), f"grad_offset({key})")
+            offs.append((off.value, n.value))
+        cache["keys"], cache["offsets"] = list(keys), offs
+    return cache["view"], cache.get("offsets")
 
 
 def _overlapped_allreduce(module, handle, dev) -> bool:
@@ -85,15 +117,12 @@ def _overlapped_allreduce(module, handle, dev) -> bool:
         return False
     lib = _lib.load()
     L = module.n_layers
-    arena, total = C.c_void_p(), C.c_int64()
-    seg = (C.c_int64 * (2 * (L + 2)))()
-    _lib.check(lib.tld_train_grad_layout(handle, C.byref(arena), C.byref(total), seg, L + 2), "tld_train_grad_layout")
-    cache = module.__dict__.setdefault("_tld_ddp", {})
-    if cache.get("ptr") != arena.value:
-        cache["ptr"] = arena.value
-        cache["view"] = torch.as_tensor(_DeviceArray(arena.value, total.value), device=dev)
+    view, _ = _grad_arena(module, handle, dev)
+    cache = _ARENA_CACHE[module]
+    seg = [v for pair in cache["segments"] for v in pair]
+    if "stream" not in cache:
         cache["stream"] = torch.cuda.Stream(device=dev)
-    view, side = cache["view"], cache["stream"]
+    side = cache["stream"]
     with torch.cuda.stream(side):
         for l in range(L - 1, -1, -1):   # the backward finishes the blocks in this order
             _lib.check(lib.tld_train_wait_grad(handle, l, side.cuda_stream), "tld_train_wait_grad")
