@@ -95,6 +95,8 @@ TLD_API int tld_op_gemm(int epi, const uint16_t* A, const uint16_t* W, int M, in
  * dW = dY^T X of the training step (tld/train.py:169 via autograd) on MN-major tcgen05 operands, no transposed copies.
  * epi 0: bf16 out, 4: fp32 out. */
 TLD_API int tld_op_gemm_mn(int epi, const uint16_t* A, const uint16_t* B, int M, int N, int K, void* out, void* stream);
+/* C[M,N] = A B with A [M,K] and B stored [K,N]: the data-gradient product dX = dY W with the weight as stored (MN-major B). */
+TLD_API int tld_op_gemm_nn(int epi, const uint16_t* A, const uint16_t* B, int M, int N, int K, void* out, void* stream);
 /* q-projection GEMM fused with the 2-key cross-attention and residual add (transformer_blocks.py:70-72,137):
  * x[M,D] += softmax2(q k0, q k1)(v0,v1) with q = A Wq^T; kv0/kv1 [rows, 2D] fp32 (K | V). */
 TLD_API int tld_op_gemm_xattn(const uint16_t* A, const uint16_t* Wq, int M, int D, float* x, const float* kv0,

@@ -86,6 +86,21 @@ def test_gemm_mn_major(lib, ctas, M, N, K):
     assert rel_fro(out, ref) < 2e-5, _err_map(out, ref)
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (8192, 3072, 768), (4096, 768, 3072), (1000, 768, 2304), (256, 192, 72)])
+@pytest.mark.parametrize("epi", [0, 4])
+def test_gemm_nn_mn_major_b(lib, ctas, M, N, K, epi):
+    """dX = dY W with W stored [K, N] (the weight as it is): K-major A, MN-major B - the dgrad shape, no transposed weight"""
+    g = torch.Generator(device="cuda").manual_seed(12)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = (torch.randn(K, N, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    ref = A.float() @ B.float()
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16 if epi == 0 else torch.float32)
+    lib.check(lib.load().tld_op_gemm_nn(epi, lib.ptr(A), lib.ptr(B), M, N, K, lib.ptr(out), _stream()), "gemm_nn")
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all(), "non-finite / unwritten outputs"
+    assert rel_fro(out.float(), ref) < (4e-3 if epi == 0 else 2e-5), _err_map(out.float(), ref)
+
+
 @pytest.mark.parametrize("M,N,K", [(256, 1024, 256), (384, 3072, 768)])
 def test_gemm_bias_bf16(lib, ctas, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(1)

@@ -524,6 +524,11 @@ int tld_op_gemm_mn(int epi, const uint16_t* A, const uint16_t* B, int M, int N, 
                         reinterpret_cast<cudaStream_t>(stream));
 }
 
+int tld_op_gemm_nn(int epi, const uint16_t* A, const uint16_t* B, int M, int N, int K, void* out, void* stream) {
+  return launch_gemm_nn(epi, reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(B), N, M, N, K, out, N,
+                        reinterpret_cast<cudaStream_t>(stream));
+}
+
 int tld_op_gemm_xattn(const uint16_t* A, const uint16_t* Wq, int M, int D, float* x, const float* kv0,
                       const float* kv1, int n_tok, void* stream) {
   XattnArgs xa;

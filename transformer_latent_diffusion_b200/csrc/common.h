@@ -45,6 +45,9 @@ int launch_gemm(int epi, const bf16* A, int lda, const bf16* W, int ldw, int M, 
 // C[M,N] = A^T B with A stored [K,M], B stored [K,N] (weight-gradient shape, K = tokens); epi = EPI_F32 or EPI_BF16
 int launch_gemm_mn(int epi, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, void* out, int ldo,
                    cudaStream_t st);
+// C[M,N] = A B with A [M,K] as usual and B stored [K,N] (data-gradient shape dX = dY W, weight untransposed)
+int launch_gemm_nn(int epi, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, void* out, int ldo,
+                   cudaStream_t st);
 
 // ---------------------------------------------------------------- rowwise.cu
 int launch_layernorm_bf16(const float* x, const float* gamma, const float* beta, bf16* y, int rows, int D,

@@ -215,33 +215,47 @@ int launch_gemm(int epi, const bf16* A, int lda, const bf16* W, int ldw, int M, 
   return dispatch(ctas, bn, epi, ta, tb, tc, M, N, K, ep, st);
 }
 
-// C[M,N] = A^T B, A stored [K, M] (row pitch lda), B stored [K, N] (row pitch ldb), both bf16; out fp32 (EPI_F32) or bf16
-// (EPI_BF16).  The weight-gradient shape dW = dY^T X: K = tokens, no transposed copies (see GemmEpi::mn_major).
-int launch_gemm_mn(int epi, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, void* out, int ldo,
-                   cudaStream_t st) {
-  TLD_CHECK(epi == EPI_F32 || epi == EPI_BF16, "launch_gemm_mn: only the plain fp32 / bf16 epilogues");
-  TLD_CHECK(M > 0 && N > 0 && K > 0, "launch_gemm_mn: empty problem");
-  TLD_CHECK(M % 8 == 0 && N % 64 == 0 && lda % 8 == 0 && ldb % 8 == 0,
-            "launch_gemm_mn: M/lda/ldb multiples of 8 and N a multiple of 64");
+// MN-major operand modes (see GemmEpi::mn_major).  a_mn: A stored [K, M] instead of [M, K]; b_mn: B stored [K, N] instead of
+// [N, K]; lda / ldb = row pitch of the stored matrix.  out fp32 (EPI_F32) or bf16 (EPI_BF16).
+static int launch_gemm_major(int epi, bool a_mn, bool b_mn, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K,
+                             void* out, int ldo, cudaStream_t st) {
+  TLD_CHECK(epi == EPI_F32 || epi == EPI_BF16, "launch_gemm_mn/nn: only the plain fp32 / bf16 epilogues");
+  TLD_CHECK(M > 0 && N > 0 && K > 0, "launch_gemm_mn/nn: empty problem");
+  TLD_CHECK(M % 8 == 0 && K % 8 == 0 && N % 64 == 0 && lda % 8 == 0 && ldb % 8 == 0,
+            "launch_gemm_mn/nn: M/K/lda/ldb multiples of 8 and N a multiple of 64");
   TLD_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
-            "launch_gemm_mn: operands must be 16-byte aligned");
+            "launch_gemm_mn/nn: operands must be 16-byte aligned");
   const bool out_f32 = epi == EPI_F32;
   TLD_CHECK((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo * (out_f32 ? 4 : 2)) % 16 == 0,
-            "launch_gemm_mn: output must be 16-byte aligned with a 16-byte multiple row pitch");
-  // a CTA pair splits the N tile in two: each half must be whole 64-column atoms
+            "launch_gemm_mn/nn: output must be 16-byte aligned with a 16-byte multiple row pitch");
+  // a CTA pair splits the N tile in two: with an MN-major B each half must be whole 64-column atoms
   int ctas = g_gemm_ctas ? g_gemm_ctas : (M >= 4096 ? 2 : 1);
   int bn = pick_bn(M, N, ctas);
-  if (ctas == 2 && (bn / 2) % 64 != 0) {
-    ctas = 1;
-    bn = pick_bn(M, N, 1);
+  if (b_mn && ctas == 2 && (bn / 2) % 64 != 0) {
+    if (N % 256 == 0 || N % 128 == 0) {
+      bn = N % 256 == 0 ? 256 : 128;   // keep the pair, take a tile whose halves are whole atoms
+    } else {
+      ctas = 1;
+      bn = pick_bn(M, N, 1);
+    }
   }
   CUtensorMap ta, tb, tc;
-  if (make_tmap_2d(&ta, A, false, K, M, lda, 64)) return 1;   // box = 64 k-rows x 64 elements
-  if (make_tmap_2d(&tb, B, false, K, N, ldb, 64)) return 1;
+  if (a_mn ? make_tmap_2d(&ta, A, false, K, M, lda, 64) : make_tmap_2d(&ta, A, false, M, K, lda, GEMM_BM)) return 1;
+  if (b_mn ? make_tmap_2d(&tb, B, false, K, N, ldb, 64) : make_tmap_2d(&tb, B, false, N, K, ldb, bn / ctas)) return 1;
   if (make_tmap_2d(&tc, out, out_f32, M, N, ldo, 32)) return 1;
   GemmEpi ep{};
-  ep.mn_major = 1;
+  ep.mn_major = (a_mn ? 1 : 0) | (b_mn ? 2 : 0);
   return dispatch(ctas, bn, epi, ta, tb, tc, M, N, K, ep, st);
+}
+// C[M,N] = A^T B: the weight-gradient shape dW = dY^T X (K = tokens)
+int launch_gemm_mn(int epi, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, void* out, int ldo,
+                   cudaStream_t st) {
+  return launch_gemm_major(epi, true, true, A, lda, B, ldb, M, N, K, out, ldo, st);
+}
+// C[M,N] = A B with B stored [K, N]: the data-gradient shape dX = dY W with the weight as it is
+int launch_gemm_nn(int epi, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, void* out, int ldo,
+                   cudaStream_t st) {
+  return launch_gemm_major(epi, false, true, A, lda, B, ldb, M, N, K, out, ldo, st);
 }
 
 static int dispatch(int ctas, int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M,

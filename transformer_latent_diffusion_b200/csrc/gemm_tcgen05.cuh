@@ -54,9 +54,10 @@ struct GemmEpi {
   // the A tile of a k-block is a 4-D TMA box [64 ch, w_box, h_box, 1] shifted by the tap, zero-filled outside.
   int conv_cpb;       // Cin / 64 (0 = plain GEMM)
   int conv_h, conv_w; // image height / width in pixels
-  // mn_major != 0: C[M,N] = A^T B with A stored [K, M] and B stored [K, N] (both row-major over K, the wgrad shape
-  // dW = dY^T X with K = tokens): operands are loaded as [64 k x 64 mn] TMA boxes and fed to tcgen05.mma as MN-major
-  // tiles (idesc a_major = b_major = 1), so no transposed copies of the activations are ever written.
+  // mn_major bit 0: A is stored [K, M], bit 1: B is stored [K, N] (row-major over K).  3 = the wgrad shape dW = dY^T X with
+  // K = tokens; 2 = the dgrad shape dX = dY W with the weight W [N_out = K, N_in = N] as it is.  Such an operand is loaded as
+  // [64 k x 64 mn] TMA boxes and fed to tcgen05.mma as an MN-major tile (idesc a/b_major = 1), so no transposed copies of
+  // activations or weights are ever written.
   int mn_major;
 };
 
@@ -182,23 +183,41 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           const int ky = tap / 3, kx = tap - 3 * ky;
           if (ep.mn_major) {
-            // MN-major operands: one [64 k-rows x 64 elements] box (8 KB, 128B-swizzled rows) per 64 columns of the tile
+            // MN-major operand (bit 0: A, bit 1: B): one [64 k-rows x 64 elements] box (8 KB, 128B-swizzled rows) per 64
+            // columns of the tile; the other operand, if K-major, takes the usual single box
+            const bool a_mn = ep.mn_major & 1, b_mn = ep.mn_major & 2;
             if constexpr (CTAS == 2) {
               if (leader) mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES * 2);
+              if (a_mn) {
 #pragma unroll
-              for (int j = 0; j < GEMM_BM / 64; ++j)
-                tma_load_2d_pair(smem_a + stage * S::A_BYTES + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, kb * GEMM_BK);
+                for (int j = 0; j < GEMM_BM / 64; ++j)
+                  tma_load_2d_pair(smem_a + stage * S::A_BYTES + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, kb * GEMM_BK);
+              } else {
+                tma_load_2d_pair(smem_a + stage * S::A_BYTES, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
+              }
+              if (b_mn) {
 #pragma unroll
-              for (int j = 0; j < BN / CTAS / 64; ++j)
-                tma_load_2d_pair(smem_b + stage * S::B_BYTES + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, kb * GEMM_BK);
+                for (int j = 0; j < BN / CTAS / 64; ++j)
+                  tma_load_2d_pair(smem_b + stage * S::B_BYTES + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, kb * GEMM_BK);
+              } else {
+                tma_load_2d_pair(smem_b + stage * S::B_BYTES, &tmap_b, &full_bar[stage], kb * GEMM_BK, n0);
+              }
             } else {
               mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+              if (a_mn) {
 #pragma unroll
-              for (int j = 0; j < GEMM_BM / 64; ++j)
-                tma_load_2d(smem_a + stage * S::A_BYTES + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, kb * GEMM_BK);
+                for (int j = 0; j < GEMM_BM / 64; ++j)
+                  tma_load_2d(smem_a + stage * S::A_BYTES + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, kb * GEMM_BK);
+              } else {
+                tma_load_2d(smem_a + stage * S::A_BYTES, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
+              }
+              if (b_mn) {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j)
-                tma_load_2d(smem_b + stage * S::B_BYTES + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, kb * GEMM_BK);
+                for (int j = 0; j < BN / 64; ++j)
+                  tma_load_2d(smem_b + stage * S::B_BYTES + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, kb * GEMM_BK);
+              } else {
+                tma_load_2d(smem_b + stage * S::B_BYTES, &tmap_b, &full_bar[stage], kb * GEMM_BK, n0);
+              }
             }
           } else if constexpr (CTAS == 2) {
             // Only the leader arms its barrier (for both CTAs' bytes).  The peer may run at most one phase ahead:
@@ -225,12 +244,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp == 1 && leader) {
     // ===================== MMA issuer (leader CTA only when paired) =====================
-    constexpr uint32_t idesc_k = umma_idesc_bf16(TILE_M, BN, 0, 0);
-    constexpr uint32_t idesc_mn = umma_idesc_bf16(TILE_M, BN, 1, 1);
-    const uint32_t idesc = ep.mn_major ? idesc_mn : idesc_k;
+    const bool a_mn = ep.mn_major & 1, b_mn = ep.mn_major & 2;
+    const uint32_t idesc = a_mn ? (b_mn ? umma_idesc_bf16(TILE_M, BN, 1, 1) : umma_idesc_bf16(TILE_M, BN, 1, 0))
+                                : (b_mn ? umma_idesc_bf16(TILE_M, BN, 0, 1) : umma_idesc_bf16(TILE_M, BN, 0, 0));
     // K-major tiles: 8-row groups 1024 B apart, +32 B per K=16 step inside the swizzle row.  MN-major tiles: 64-wide
     // column atoms 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO), +16 k-rows = 2048 B per K=16 step.
-    const uint32_t lbo = ep.mn_major ? 8192u : 16u, kstep = ep.mn_major ? 128u : 2u;
+    const uint32_t lbo_a = a_mn ? 8192u : 16u, kstep_a = a_mn ? 128u : 2u;
+    const uint32_t lbo_b = b_mn ? 8192u : 16u, kstep_b = b_mn ? 128u : 2u;
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -244,13 +264,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t adesc = umma_smem_desc_sw128(smem_u32(smem_a + stage * S::A_BYTES), lbo, 1024);
-          const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(smem_b + stage * S::B_BYTES), lbo, 1024);
+          const uint64_t adesc = umma_smem_desc_sw128(smem_u32(smem_a + stage * S::A_BYTES), lbo_a, 1024);
+          const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(smem_b + stage * S::B_BYTES), lbo_b, 1024);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / UMMA_K; ++k) {
             // advance 32 B (16 bf16) along K inside the 128 B swizzle row: +2 in the (addr>>4) field
-            if constexpr (CTAS == 2) umma_ss_f16_pair(d_tmem, adesc + kstep * k, bdesc + kstep * k, idesc, (kb | k) != 0);
-            else umma_ss_f16(d_tmem, adesc + kstep * k, bdesc + kstep * k, idesc, (kb | k) != 0);
+            if constexpr (CTAS == 2) umma_ss_f16_pair(d_tmem, adesc + kstep_a * k, bdesc + kstep_b * k, idesc, (kb | k) != 0);
+            else umma_ss_f16(d_tmem, adesc + kstep_a * k, bdesc + kstep_b * k, idesc, (kb | k) != 0);
           }
           if constexpr (CTAS == 2) {
             umma_commit_pair(&empty_bar[stage]);                      // frees this stage in BOTH CTAs

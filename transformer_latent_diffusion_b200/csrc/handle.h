@@ -75,12 +75,7 @@ struct tld_denoiser {
     float *xs0, *xs1, *xs2;        // residual stream before self-attn / cross-attn / MLP, fp32 [T,D]
     bf16 *qkv, *hid, *hid2;        // saved GEMM outputs
   };
-  struct TrainWeightsT {           // transposed bf16 copies for dgrad (refreshed by tld_denoiser_set_param)
-    bf16 *wqkvT, *wqT, *wupT, *wdownT;
-  };
   std::vector<TrainLayer> tl;
-  std::vector<TrainWeightsT> wT;
-  bf16* wkv_allT = nullptr;        // [D, L*2D]
   int train_batch = 0;
   std::vector<void*> train_allocs;
   std::map<std::string, std::pair<float*, long long>> grads;  // reference-layout fp32 gradient of every parameter

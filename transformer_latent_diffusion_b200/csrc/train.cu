@@ -3,7 +3,7 @@
 // d(loss)/d(pred) into the fp32 gradient of every parameter in the reference's state_dict layout.
 //
 // Tensor-core work: every dgrad / wgrad is the tcgen05 GEMM of gemm_tcgen05.cuh on bf16 operands
-//   dgrad  dX[T,K]  = dY[T,N] * W[N,K]          -> launch_gemm(A = dY, W = W^T (kept transposed copy))
+//   dgrad  dX[T,K]  = dY[T,N] * W[N,K]          -> launch_gemm_nn(A = dY, B = W as stored): MN-major B operand
 //   wgrad  dW[N,K]  = dY^T[N,T] * X[T,K]        -> launch_gemm_mn(A = dY, B = X): MN-major operands, no transposes
 // Everything else is the HBM-bound kernels of backward.cu / attention_bwd.cu plus a few tiny fp32 products for the
 // 16-wide patch/out projections and the B-row conditioning path.  The residual-stream gradient stays fp32.
@@ -202,17 +202,6 @@ static int ensure_train(tld_denoiser* h, int B) {
       h->grads[kv.first] = {h->grad_arena + off, kv.second.numel};
       off += kv.second.numel;
     }
-    h->wT.resize(L);
-    for (int l = 0; l < L; ++l) {
-      void* q;
-      TLD_CUDA_OK(cudaMalloc(&q, sizeof(bf16) * 3LL * D * D)); h->wT[l].wqkvT = (bf16*)q;
-      TLD_CUDA_OK(cudaMalloc(&q, sizeof(bf16) * 1LL * D * D)); h->wT[l].wqT = (bf16*)q;
-      TLD_CUDA_OK(cudaMalloc(&q, sizeof(bf16) * 1LL * H4 * D)); h->wT[l].wupT = (bf16*)q;
-      TLD_CUDA_OK(cudaMalloc(&q, sizeof(bf16) * 1LL * H4 * D)); h->wT[l].wdownT = (bf16*)q;
-    }
-    void* q;
-    TLD_CUDA_OK(cudaMalloc(&q, sizeof(bf16) * 2LL * L * D * D));
-    h->wkv_allT = (bf16*)q;
   }
   if (B <= h->train_batch) return 0;
   TLD_CUDA_OK(cudaDeviceSynchronize());
@@ -241,18 +230,6 @@ static int ensure_train(tld_denoiser* h, int B) {
   return 0;
 }
 
-static int refresh_transposed_weights(tld_denoiser* h, cudaStream_t st) {
-  const int D = h->D, H4 = h->H4, L = h->L;
-  for (int l = 0; l < L; ++l) {
-    const auto& ly = h->layers[l];
-    if (launch_transpose_bf16(ly.wqkv, h->wT[l].wqkvT, 3 * D, D, st)) return 1;   // [3D,D] -> [D,3D]
-    if (launch_transpose_bf16(ly.wq, h->wT[l].wqT, D, D, st)) return 1;
-    if (launch_transpose_bf16(ly.wup, h->wT[l].wupT, H4, D, st)) return 1;        // [4D,D] -> [D,4D]
-    if (launch_transpose_bf16(ly.wdown, h->wT[l].wdownT, D, H4, st)) return 1;    // [D,4D] -> [4D,D]
-  }
-  return launch_transpose_bf16(h->wkv_all, h->wkv_allT, 2 * L * D, D, st);          // [L2D, D] -> [D, L2D]
-}
-
 }  // namespace tld
 
 extern "C" {
@@ -269,7 +246,6 @@ TLD_API int tld_train_forward(tld_denoiser* h, const float* x, const float* nois
   const int T = B * N;
   if (tld_internal_ensure(h, B, 2 * B)) return 1;
   if (ensure_train(h, B)) return 1;
-  if (refresh_transposed_weights(h, st)) return 1;
   const long long kvs = 2LL * L * D;
   float* s_label = h->t_small;  // [B, Te] copy of the labels for the label_proj wgrad
   TLD_CUDA_OK(cudaMemcpyAsync(s_label, label, sizeof(float) * (size_t)B * h->Te, cudaMemcpyDeviceToDevice, st));
@@ -335,13 +311,12 @@ TLD_API int tld_train_backward(tld_denoiser* h, const float* d_pred, int batch, 
 
   for (int l = L - 1; l >= 0; --l) {
     const auto& ly = h->layers[l];
-    const auto& wt = h->wT[l];
     auto& t = h->tl[l];
     const std::string b = tb + "decoder_blocks." + std::to_string(l) + ".";
     // ================= MLPSepConv: x3 = x2 + conv1x1(gelu(dwconv(conv1x1(LN3 x2)))) =================
     if (launch_cast_transpose_f32(h->t_dx, h->t_a, nullptr, T, D, st)) return 1;                     // dy -> bf16
     if (launch_colsum_f32(h->t_dx, G(h, b + "mlp.mlp.3.bias"), T, D, 0, st)) return 1;
-    if (launch_gemm(EPI_BF16, h->t_a, D, wt.wdownT, D, T, H4, D, h->t_big, H4, nullptr, nullptr, st)) return 1;   // d_hid2
+    if (launch_gemm_nn(EPI_BF16, h->t_a, D, ly.wdown, H4, T, H4, D, h->t_big, H4, st)) return 1;   // d_hid2 = dy W_down
     if (launch_gemm_mn(EPI_F32, h->t_a, D, t.hid2, H4, D, H4, T, G(h, b + "mlp.mlp.3.weight"), H4, st)) return 1;  // dy^T hid2
     float* dw9 = reinterpret_cast<float*>(h->t_xnT);  // [9, H4] scratch
     if (launch_dwconv_gelu_bwd(t.hid, h->t_big, ly.dww9, ly.dwb, h->t_big2, h->t_big, dw9, G(h, b + "mlp.mlp.1.bias"), B, h->G, H4,
@@ -352,7 +327,7 @@ TLD_API int tld_train_backward(tld_denoiser* h, const float* d_pred, int batch, 
     if (launch_colsum_bf16(h->t_big, G(h, b + "mlp.mlp.0.bias"), T, H4, 0, st)) return 1;
     if (launch_layernorm_bf16(t.xs2, ly.ln3w, ly.ln3b, h->xn, T, D, st)) return 1;                  // recompute LN3(x2)
     if (launch_gemm_mn(EPI_F32, h->t_big, H4, h->xn, D, H4, D, T, G(h, b + "mlp.mlp.0.weight"), D, st)) return 1;  // d_hid^T xn
-    if (launch_gemm(EPI_F32, h->t_big, H4, wt.wupT, H4, T, D, H4, h->t_dxn, D, nullptr, nullptr, st)) return 1;      // d LN3 out
+    if (launch_gemm_nn(EPI_F32, h->t_big, H4, ly.wup, D, T, D, H4, h->t_dxn, D, st)) return 1;      // d LN3 out = d_hid W_up
     if (launch_layernorm_bwd(h->t_dxn, t.xs2, ly.ln3w, h->t_dx, G(h, b + "norm3.weight"), G(h, b + "norm3.bias"), T, D, st)) return 1;
     // ================= cross-attention: x2 = x1 + CA(LN2 x1, y) =================
     if (launch_layernorm_bf16(t.xs1, ly.ln2w, ly.ln2b, h->xn, T, D, st)) return 1;
@@ -361,14 +336,14 @@ TLD_API int tld_train_backward(tld_denoiser* h, const float* d_pred, int batch, 
                          h->t_dkv + (size_t)l * 2 * D, h->t_dkv + (size_t)B * kvs + (size_t)l * 2 * D, kvs, B, N, D, st))
       return 1;
     if (launch_gemm_mn(EPI_F32, h->t_a, D, h->xn, D, D, D, T, G(h, b + "cross_attention.q_linear.weight"), D, st)) return 1;  // dq^T xn
-    if (launch_gemm(EPI_F32, h->t_a, D, wt.wqT, D, T, D, D, h->t_dxn, D, nullptr, nullptr, st)) return 1;
+    if (launch_gemm_nn(EPI_F32, h->t_a, D, ly.wq, D, T, D, D, h->t_dxn, D, st)) return 1;           // d LN2 out = dq W_q
     if (launch_layernorm_bwd(h->t_dxn, t.xs1, ly.ln2w, h->t_dx, G(h, b + "norm2.weight"), G(h, b + "norm2.bias"), T, D, st)) return 1;
     // ================= self-attention: x1 = x0 + Attn(qkv(LN1 x0)) =================
     if (launch_self_attention_bwd(t.qkv, h->t_dx, t.xs0, t.xs1, h->t_big, B, N, D, st)) return 1;   // dqkv [T,3D]
     if (launch_layernorm_bf16(t.xs0, ly.ln1w, ly.ln1b, h->xn, T, D, st)) return 1;
     if (launch_gemm_mn(EPI_F32, h->t_big, 3 * D, h->xn, D, 3 * D, D, T, G(h, b + "self_attention.qkv_linear.weight"), D, st))
       return 1;                                                                                     // dqkv^T xn
-    if (launch_gemm(EPI_F32, h->t_big, 3 * D, wt.wqkvT, 3 * D, T, D, 3 * D, h->t_dxn, D, nullptr, nullptr, st)) return 1;
+    if (launch_gemm_nn(EPI_F32, h->t_big, 3 * D, ly.wqkv, D, T, D, 3 * D, h->t_dxn, D, st)) return 1;   // d LN1 out = dqkv W_qkv
     if (launch_layernorm_bwd(h->t_dxn, t.xs0, ly.ln1w, h->t_dx, G(h, b + "norm1.weight"), G(h, b + "norm1.bias"), T, D, st)) return 1;
     TLD_CUDA_OK(cudaEventRecord(h->ev_grad[l], st));   // this layer's gradients (all but kv_linear) are final
   }
@@ -393,7 +368,7 @@ TLD_API int tld_train_backward(tld_denoiser* h, const float* d_pred, int batch, 
   // ---- conditioning path (denoiser.py:117-122): rows [0,B) noise tokens, [B,2B) label tokens
   cast_pad_kernel<<<blocks((long long)R8 * kvs), 256, 0, st>>>(h->t_dkv, c_dkvb, c_dkvT, 2 * B, R8, int(kvs));
   TLD_CUDA_OK(cudaGetLastError());
-  if (launch_gemm(EPI_F32, c_dkvb, int(kvs), h->wkv_allT, int(kvs), R8, D, int(kvs), c_dy, D, nullptr, nullptr, st)) return 1;  // d y
+  if (launch_gemm_nn(EPI_F32, c_dkvb, int(kvs), h->wkv_all, D, R8, D, int(kvs), c_dy, D, st)) return 1;  // d y = dkv W_kv
   bf16_pad_transpose_kernel<<<blocks((long long)R8 * D), 256, 0, st>>>(h->ycond, c_ycT, 2 * B, R8, D);
   TLD_CUDA_OK(cudaGetLastError());
   if (launch_gemm(EPI_F32, c_dkvT, R8, c_ycT, R8, int(kvs), D, R8, G(h, tb + "decoder_blocks.0.cross_attention.kv_linear.weight"), D,
