@@ -63,6 +63,12 @@ TLD_API void tld_denoiser_destroy(tld_denoiser* h);
  * (e.g. "denoiser_trans_block.decoder_blocks.0.mlp.mlp.1.weight"); `data` is fp32 (host or device pointer,
  * `numel` elements).  The library copies/packs into its own arena (bf16 for GEMM operands, fp32 otherwise). */
 TLD_API int tld_denoiser_set_param(tld_denoiser* h, const char* key, const float* data, int64_t numel);
+/* The same for n parameters at once from DEVICE-resident fp32 tensors, enqueued on `stream` without any host
+ * synchronisation (copies / conversion kernels straight from the sources).  The Python mirror calls it before every forward,
+ * generate and training step: in-place updates by optimisers and EMA code are not reliably visible in torch's version
+ * counters (fused Adam; `.data` arithmetic as in tld/train.py:55-58), so the packed copy is refreshed, not cached. */
+TLD_API int tld_denoiser_set_params_async(tld_denoiser* h, int n, const char* const* keys, const float* const* data,
+                                          const int64_t* numels, void* stream);
 /* Number of parameters still missing after the set_param calls (0 = ready). */
 TLD_API int tld_denoiser_missing_params(tld_denoiser* h);
 

@@ -154,3 +154,60 @@ def test_sampler_repeatable_and_stats():
         assert rel_fro(a, ref) < 3 * TOL, (n_iter, exponent, rel_fro(a, ref))
     ms, launches = gen.last_stats()
     assert ms > 0 and launches == 50 * (9 * 1 + 4) + 3
+
+
+def test_in_place_weight_updates_are_always_seen():
+    """Parameters change under the library's feet in ways torch's version counters do not record: the reference's own
+    EMA update works on `.data` (tld/train.py:55-58) and torch.optim.Adam(fused=True) leaves `_version` untouched.
+    The packed weights are therefore refreshed on every call; forward and sampler must follow the current values."""
+    cfg = O.OracleCfg(image_size=16, embed_dim=128, n_layers=2)
+    sd = O.synth_state_dict(cfg, 21)
+    g = torch.Generator().manual_seed(3)
+    x, t, lab = torch.randn(2, 4, 16, 16, generator=g), torch.rand(2, 1, generator=g), torch.randn(2, 768, generator=g)
+    m = _model(cfg, sd)
+    with torch.no_grad():
+        out0 = m(x.cuda(), t.cuda(), lab.cuda())
+        versions = [p._version for p in m.parameters()]
+        # the reference's EMA arithmetic: every parameter moves, no version counter does
+        for p in m.parameters():
+            p.data.mul_(0.9).add_(torch.full_like(p, 0.01), alpha=0.1)
+        assert [p._version for p in m.parameters()] == versions
+        out1 = m(x.cuda(), t.cuda(), lab.cuda())
+        sd1 = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+        ref1 = O.denoiser_forward(sd1, cfg, x, t, lab)
+    assert rel_fro(out0, ref1) > 5 * TOL, "the perturbation is too small to tell stale weights from fresh ones"
+    assert rel_fro(out1, ref1) < TOL
+    # the sampler reads the same packed weights
+    from transformer_latent_diffusion_b200.diffusion import DiffusionGenerator
+    from oracle.ref_loader import IdentityVAE
+
+    gen = DiffusionGenerator(m, IdentityVAE(), torch.device("cuda"), torch.float32)
+    labels = torch.randn(2, 768, generator=g)
+    seeds = torch.randn(2, 4, 16, 16, generator=g)
+    lat_a = gen.generate_latents(labels.cuda(), n_iter=4, num_imgs=2, class_guidance=3.0, img_size=16, seeds=seeds.cuda())
+    with torch.no_grad():
+        for p in m.parameters():
+            p.data.mul_(1.05)
+    lat_b = gen.generate_latents(labels.cuda(), n_iter=4, num_imgs=2, class_guidance=3.0, img_size=16, seeds=seeds.cuda())
+    sd2 = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    ref_b = O.generate_latents(sd2, cfg, labels, seeds, n_iter=4, class_guidance=3.0)
+    assert rel_fro(lat_b, ref_b) < TOL and rel_fro(lat_a, ref_b) > TOL
+
+
+def test_fused_adam_training_uses_fresh_weights():
+    """two optimiser steps with torch.optim.Adam(fused=True): the second forward must see the first step's update"""
+    cfg = O.OracleCfg(image_size=16, embed_dim=128, n_layers=1)
+    sd = O.synth_state_dict(cfg, 22)
+    g = torch.Generator().manual_seed(4)
+    x, t, lab = torch.randn(4, 4, 16, 16, generator=g), torch.rand(4, 1, generator=g), torch.randn(4, 768, generator=g)
+    m = _model(cfg, sd).train()
+    opt = torch.optim.Adam(m.parameters(), lr=5e-2, fused=True)   # large steps: stale weights would be obvious
+    for _ in range(2):
+        opt.zero_grad()
+        loss = torch.nn.functional.mse_loss(m(x.cuda(), t.cuda(), lab.cuda()), x.cuda())
+        loss.backward()
+        opt.step()
+    with torch.no_grad():
+        out = m.eval()(x.cuda(), t.cuda(), lab.cuda())
+        ref = O.denoiser_forward({k: v.detach().cpu() for k, v in m.state_dict().items()}, cfg, x, t, lab)
+    assert rel_fro(out, ref) < TOL

@@ -34,6 +34,8 @@ PROTOTYPES = {
     "tld_denoiser_create": (C.c_int, [C.POINTER(TldConfig), C.c_int, C.POINTER(C.c_void_p)]),
     "tld_denoiser_destroy": (None, [C.c_void_p]),
     "tld_denoiser_set_param": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
+    "tld_denoiser_set_params_async": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p),
+                                                C.POINTER(C.c_int64), C.c_void_p]),
     "tld_denoiser_missing_params": (C.c_int, [C.c_void_p]),
     "tld_denoiser_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                        C.c_void_p]),

@@ -47,6 +47,33 @@ __global__ void transpose_f32_kernel(const float* __restrict__ s, float* __restr
   }
 }
 
+// all parameter slots of one refresh in a few launches: blockIdx.y = entry, blockIdx.x strides over its elements
+struct RefreshEntry {
+  const float* src;
+  void* dst;
+  long long numel;
+  int kind, rows, cols, pad;   // kind: 0 copy fp32, 1 fp32 -> bf16, 2 fp32 [rows, cols] -> fp32 [cols, rows]
+};
+constexpr int REFRESH_BATCH = 96;   // 96 x 40 B = 3840 B of kernel arguments
+struct RefreshBatch {
+  RefreshEntry e[REFRESH_BATCH];
+};
+__global__ void __launch_bounds__(256) refresh_params_kernel(const __grid_constant__ RefreshBatch batch) {
+  const RefreshEntry& e = batch.e[blockIdx.y];
+  const long long stride = (long long)gridDim.x * 256;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < e.numel; i += stride) {
+    const float v = e.src[i];
+    if (e.kind == 0) {
+      reinterpret_cast<float*>(e.dst)[i] = v;
+    } else if (e.kind == 1) {
+      reinterpret_cast<bf16*>(e.dst)[i] = __float2bfloat16(v);
+    } else {
+      const int r = int(i / e.cols), c = int(i % e.cols);
+      reinterpret_cast<float*>(e.dst)[(size_t)c * e.rows + r] = v;
+    }
+  }
+}
+
 }  // namespace tld
 
 #include "handle.h"
@@ -345,6 +372,47 @@ int tld_denoiser_set_param(tld_denoiser* h, const char* key, const float* data, 
   }
   s.filled = true;
   return 0;
+}
+
+// Bulk, asynchronous refresh of the packed weights from DEVICE-resident fp32 tensors, enqueued on `stream` with no host
+// synchronisation: plain copies for the fp32 slots, one conversion kernel per bf16 / transposed slot straight from the source.
+// The Python mirror calls this before EVERY forward / generate / training step: parameters are modified in place by
+// optimisers and EMA updates in ways torch's version counters do not always record (fused Adam, `.data` arithmetic as in
+// tld/train.py:55-58), so a cached copy can never be trusted; the refresh costs one pass over the weights (~0.15 ms).
+int tld_denoiser_set_params_async(tld_denoiser* h, int n, const char* const* keys, const float* const* data,
+                                  const int64_t* numels, void* stream) {
+  TLD_CHECK(h && keys && data && numels && n >= 0, "tld_denoiser_set_params_async: bad argument");
+  TLD_CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  RefreshBatch batch;
+  int filled = 0;
+  auto flush = [&]() -> int {
+    if (filled == 0) return 0;
+    refresh_params_kernel<<<dim3(64, filled), 256, 0, st>>>(batch);
+    TLD_CUDA_OK(cudaGetLastError());
+    filled = 0;
+    return 0;
+  };
+  for (int i = 0; i < n; ++i) {
+    TLD_CHECK(keys[i] && data[i], "tld_denoiser_set_params_async: null entry");
+    auto it = h->slots.find(keys[i]);
+    if (it == h->slots.end()) return fail(std::string("unexpected state_dict key: ") + keys[i]);
+    Slot& s = it->second;
+    if (numels[i] != s.numel)
+      return fail(std::string("size mismatch for ") + keys[i] + ": got " + std::to_string(numels[i]) + ", expected " +
+                  std::to_string(s.numel));
+    RefreshEntry& e = batch.e[filled++];
+    e.src = data[i];
+    e.dst = s.dst;
+    e.numel = s.numel;
+    e.kind = s.kind == P_F32 ? 0 : (s.kind == P_BF16 ? 1 : 2);
+    e.rows = s.rows;
+    e.cols = s.cols > 0 ? s.cols : 1;
+    e.pad = 0;
+    s.filled = true;
+    if (filled == REFRESH_BATCH && flush()) return 1;
+  }
+  return flush();
 }
 
 int tld_denoiser_missing_params(tld_denoiser* h) {

@@ -136,7 +136,7 @@ class Denoiser(nn.Module):
         # library state (never part of state_dict / deepcopy)
         self.__dict__["_handle"] = None
         self.__dict__["_handle_device"] = None
-        self.__dict__["_synced"] = None
+        self.__dict__["_checked_complete"] = False
 
     # ------------------------------------------------------------------ library handle management
     def __deepcopy__(self, memo):
@@ -180,19 +180,35 @@ class Denoiser(nn.Module):
             _lib.check(lib.tld_denoiser_create(C.byref(cfg), idx, C.byref(h)), "tld_denoiser_create")
             self.__dict__["_handle"] = h
             self.__dict__["_handle_device"] = idx
-            self.__dict__["_synced"] = None
-        # refresh the packed weights when any parameter was replaced or modified in place
-        sig = tuple((t.data_ptr(), t._version) for _, t in self._float_entries())
-        if sig != self.__dict__["_synced"]:
-            h = self.__dict__["_handle"]
-            for key, t in self._float_entries():
-                src = t.detach().to(dtype=torch.float32).contiguous()
-                _lib.check(lib.tld_denoiser_set_param(h, key.encode(), _lib.ptr(src), src.numel()),
-                           f"tld_denoiser_set_param({key})")
+            self.__dict__["_checked_complete"] = False
+        # Refresh the packed (bf16 / transposed) weights from the fp32 parameters on EVERY call, asynchronously on the
+        # current stream.  A cached copy cannot be trusted: in-place updates are not reliably visible in torch's version
+        # counters (torch.optim.Adam(fused=True) leaves them untouched, and so does the reference's own
+        # `ema_param.data.mul_(alpha).add_(...)`, tld/train.py:55-58).  One pass over the weights, ~0.15 ms on a B200.
+        h = self.__dict__["_handle"]
+        dev = torch.device("cuda", idx)
+        entries = list(self._float_entries())
+        keys = tuple(k for k, _ in entries)
+        cache = self.__dict__.get("_key_arrays")
+        if cache is None or cache[0] != keys:
+            arr = (C.c_char_p * len(keys))(*[k.encode() for k in keys])
+            cache = (keys, arr, (C.c_int64 * len(keys))(*[t.numel() for _, t in entries]))
+            self.__dict__["_key_arrays"] = cache
+        srcs = []
+        for _, t in entries:
+            s = t.detach()
+            if s.device != dev or s.dtype != torch.float32 or not s.is_contiguous():
+                s = s.to(device=dev, dtype=torch.float32).contiguous()   # temporary, ordered on the same stream
+            srcs.append(s)
+        ptrs = (C.c_void_p * len(srcs))(*[s.data_ptr() for s in srcs])
+        with torch.cuda.device(dev):
+            _lib.check(lib.tld_denoiser_set_params_async(h, len(srcs), cache[1], ptrs, cache[2], _lib.current_stream_ptr(dev)),
+                       "tld_denoiser_set_params_async")
+        if not self.__dict__.get("_checked_complete"):
             missing = lib.tld_denoiser_missing_params(h)
             if missing:
                 raise _lib.TldError(f"{missing} parameters were not provided to the library")
-            self.__dict__["_synced"] = sig
+            self.__dict__["_checked_complete"] = True
         return self.__dict__["_handle"]
 
     # ------------------------------------------------------------------ forward
