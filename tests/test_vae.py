@@ -271,3 +271,33 @@ def test_encode_gpu_matches_oracle_and_roundtrip():
     dec = AutoencoderKLDecoder(block_out=(128, 128, 256, 256)).cuda().to(torch.bfloat16)
     out = decode_latents(back, dec)
     assert out.shape == (3, 3, 64, 64) and out.min() >= 0 and out.max() <= 1
+
+
+def test_vae_caches_follow_load_state_dict():
+    """weights loaded AFTER a first decode must be used (the packed / fp32 copies are keyed on the parameter's storage and
+    version): a fresh module with the same weights gives the same image"""
+    m = _small()
+    z = torch.randn(1, 4, 8, 8)
+    m.decode(z)
+    donor = _small()
+    with torch.no_grad():
+        for p in donor.parameters():
+            p.mul_(1.3)
+    m.load_state_dict(donor.state_dict())
+    (a,), (b,) = m.decode(z), donor.decode(z)
+    assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_vae_gpu_caches_follow_load_state_dict():
+    """the same on the CUDA/bf16 path, where the repacked conv weights and fp32 norm parameters are cached"""
+    from transformer_latent_diffusion_b200.vae import AutoencoderKLDecoder
+
+    torch.manual_seed(5)
+    m = AutoencoderKLDecoder(block_out=(128, 128, 256, 256)).cuda().to(torch.bfloat16)
+    donor = AutoencoderKLDecoder(block_out=(128, 128, 256, 256)).cuda().to(torch.bfloat16)
+    z = torch.randn(2, 4, 8, 8, device="cuda")
+    m.decode(z)                      # fills the caches with m's initial weights
+    m.load_state_dict(donor.state_dict())
+    (a,), (b,) = m.decode(z), donor.decode(z)
+    assert torch.equal(a, b)

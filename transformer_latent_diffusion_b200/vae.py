@@ -131,11 +131,13 @@ class AutoencoderKLDecoder(nn.Module):
             w = self._p(name + ".weight")
             cout, cin = w.shape[0], w.shape[1]
             cache = self.__dict__.setdefault("_wpack_cache", {})
-            wp = cache.get(name)
-            if wp is None or wp.device != x.device:
+            sig = (w.data_ptr(), w._version, x.device)   # load_state_dict / .to() after a first decode must repack
+            ent = cache.get(name)
+            if ent is None or ent[0] != sig:
                 # [Cout, Cin, 3, 3] -> [Cout, (ky, kx, cin)] bf16: the K order the implicit GEMM walks
-                wp = w.detach().permute(0, 2, 3, 1).reshape(cout, 9 * cin).to(torch.bfloat16).contiguous()
-                cache[name] = wp
+                ent = (sig, w.detach().permute(0, 2, 3, 1).reshape(cout, 9 * cin).to(torch.bfloat16).contiguous())
+                cache[name] = ent
+            wp = ent[1]
             x = x.contiguous(memory_format=torch.channels_last)
             B, _, H, W = x.shape
             y = torch.empty((B, cout, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
@@ -149,11 +151,13 @@ class AutoencoderKLDecoder(nn.Module):
     def _f32(self, key: str, device) -> torch.Tensor:
         """fp32 copy of a 1-D parameter for the fused kernels (cached per device)"""
         cache = self.__dict__.setdefault("_f32_cache", {})
-        t = cache.get(key)
-        if t is None or t.device != device:
-            t = self._p(key).detach().to(device=device, dtype=torch.float32).contiguous()
-            cache[key] = t
-        return t
+        p = self._p(key)
+        sig = (p.data_ptr(), p._version, device)
+        ent = cache.get(key)
+        if ent is None or ent[0] != sig:
+            ent = (sig, p.detach().to(device=device, dtype=torch.float32).contiguous())
+            cache[key] = ent
+        return ent[1]
 
     @staticmethod
     def _fusable(x) -> bool:
