@@ -297,7 +297,8 @@ def test_vae_gpu_caches_follow_load_state_dict():
     m = AutoencoderKLDecoder(block_out=(128, 128, 256, 256)).cuda().to(torch.bfloat16)
     donor = AutoencoderKLDecoder(block_out=(128, 128, 256, 256)).cuda().to(torch.bfloat16)
     z = torch.randn(2, 4, 8, 8, device="cuda")
-    m.decode(z)                      # fills the caches with m's initial weights
+    (before,) = m.decode(z)          # fills the caches with m's initial weights
     m.load_state_dict(donor.state_dict())
     (a,), (b,) = m.decode(z), donor.decode(z)
-    assert torch.equal(a, b)
+    # same weights -> same image up to library-kernel run-to-run differences; stale caches would give `before` again
+    assert rel_fro(a, b) < 1e-2 and rel_fro(a, before) > 0.3
