@@ -210,10 +210,19 @@ def run_b200(args) -> None:
         import torch.distributed as dist_mod
 
         dist = dist_mod
-        # stdout carries exactly one JSON line: whatever NCCL_DEBUG the environment sets (the "NCCL version ..." banner
-        # goes to stdout by default) is sent to stderr instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: NCCL prints its "NCCL version ..." banner to stdout when the first
+        # communicator is created, so file descriptor 1 points at stderr while that happens
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     B = args.batch  # images per GPU per step (weak scaling: fixed per-GPU work)
     torch.manual_seed(0)
