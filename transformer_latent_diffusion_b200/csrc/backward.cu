@@ -51,12 +51,6 @@ int launch_cast_transpose_f32(const float* in, bf16* out, bf16* outT, int R, int
   TLD_CUDA_OK(cudaGetLastError());
   return 0;
 }
-int launch_transpose_bf16(const bf16* in, bf16* outT, int R, int C, cudaStream_t st) {
-  dim3 grid((C + 63) / 64, (R + 63) / 64);
-  cast_transpose_kernel<bf16><<<grid, 256, 0, st>>>(in, nullptr, outT, R, C);
-  TLD_CUDA_OK(cudaGetLastError());
-  return 0;
-}
 
 // ------------------------------------------------------------------------------------------------
 // column sums: out[c] (+)= sum_r in[r, c]; deterministic (fixed row partition, fixed reduction order)

@@ -16,7 +16,6 @@
 namespace tld {
 
 int launch_cast_transpose_f32(const float* in, bf16* out, bf16* outT, int R, int C, cudaStream_t st);
-int launch_transpose_bf16(const bf16* in, bf16* outT, int R, int C, cudaStream_t st);
 int launch_colsum_f32(const float* in, float* out, int R, int C, int accumulate, cudaStream_t st);
 int launch_colsum_bf16(const bf16* in, float* out, int R, int C, int accumulate, cudaStream_t st);
 int launch_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
