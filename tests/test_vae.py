@@ -301,4 +301,6 @@ def test_vae_gpu_caches_follow_load_state_dict():
     m.load_state_dict(donor.state_dict())
     (a,), (b,) = m.decode(z), donor.decode(z)
     # same weights -> same image up to library-kernel run-to-run differences; stale caches would give `before` again
-    assert rel_fro(a, b) < 1e-2 and rel_fro(a, before) > 0.3
+    # (two instances go through cuDNN/cuBLAS for conv_in/conv_out/attention: algorithm choices differ at the bf16 level,
+    #  a few 1e-3 .. 1e-2 after 30 layers; unrelated weights differ by O(1))
+    assert rel_fro(a, b) < 5e-2 and rel_fro(a, before) > 0.3

@@ -7,6 +7,10 @@
 #include <vector>
 
 #include "../../include/tld_b200.h"
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.h"
 #include "gemm_tcgen05.cuh"  // EpiMode
 #include "launch.h"
@@ -23,6 +27,25 @@ const char* last_error() { return g_err.c_str(); }
 static int g_pdl = 0;  // measured on B200: no gain (the step is power-capped, not launch-gap bound); kept as an option
 void set_pdl(int v) { g_pdl = v; }
 bool pdl_enabled() { return g_pdl != 0; }
+
+float* device_scratch(ScratchSlot slot, size_t n_floats) {
+  struct Buf { float* p = nullptr; size_t cap = 0; };
+  static std::mutex mu;
+  static std::map<std::pair<int, int>, Buf> bufs;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { fail("device_scratch: cudaGetDevice failed"); return nullptr; }
+  std::lock_guard<std::mutex> lock(mu);
+  Buf& b = bufs[{dev, (int)slot}];
+  if (n_floats > b.cap) {
+    if (b.p) cudaFree(b.p);   // synchronises with any kernel still reading the old buffer
+    b.p = nullptr;
+    b.cap = 0;
+    const size_t want = n_floats + n_floats / 4;   // some head room: batch sizes creep up during warm-up
+    if (cudaMalloc(&b.p, want * sizeof(float)) != cudaSuccess) { fail("device_scratch: cudaMalloc failed"); return nullptr; }
+    b.cap = want;
+  }
+  return b.p;
+}
 
 int sm_count() {
   static int n = 0;

@@ -86,8 +86,6 @@ __global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restr
   for (int k = 0; k < nchunk; ++k) t += partial[(size_t)k * C + c];
   out[c] = accumulate ? out[c] + t : t;
 }
-static float* g_colsum_partial = nullptr;
-static size_t g_colsum_cap = 0;
 template <typename TIn>
 static int colsum_launch(const TIn* in, float* out, int R, int C, int accumulate, cudaStream_t st) {
   int nchunk = (R + 127) / 128;
@@ -96,12 +94,8 @@ static int colsum_launch(const TIn* in, float* out, int R, int C, int accumulate
   const int rpc = (((R + nchunk - 1) / nchunk) + 7) / 8 * 8;
   nchunk = (R + rpc - 1) / rpc;
   if (nchunk < 1) nchunk = 1;
-  const size_t need = (size_t)nchunk * C;
-  if (need > g_colsum_cap) {
-    if (g_colsum_partial) cudaFree(g_colsum_partial);
-    TLD_CUDA_OK(cudaMalloc(&g_colsum_partial, need * sizeof(float)));
-    g_colsum_cap = need;
-  }
+  float* g_colsum_partial = device_scratch(SCR_COLSUM, (size_t)nchunk * C);
+  if (!g_colsum_partial) return 1;
   colsum_kernel<TIn><<<dim3((C + 31) / 32, nchunk), 256, 0, st>>>(in, g_colsum_partial, R, C, rpc);
   TLD_CUDA_OK(cudaGetLastError());
   colsum_reduce_kernel<<<(C + 255) / 256, 256, 0, st>>>(g_colsum_partial, out, nchunk, C, accumulate);
@@ -217,19 +211,13 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
   else dbeta[c - D] = t;
 }
 
-static float* g_ln_partial = nullptr;
-static size_t g_ln_partial_cap = 0;
 
 int launch_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
                          int rows, int D, cudaStream_t st) {
   TLD_CHECK(D % 128 == 0 && D >= 128 && D <= 1024, "layernorm_bwd: embed_dim must be a multiple of 128 in [128,1024]");
   const int nblk = (rows + 63) / 64;
-  const size_t need = (size_t)nblk * 2 * D;
-  if (need > g_ln_partial_cap) {
-    if (g_ln_partial) cudaFree(g_ln_partial);
-    TLD_CUDA_OK(cudaMalloc(&g_ln_partial, need * sizeof(float)));
-    g_ln_partial_cap = need;
-  }
+  float* g_ln_partial = device_scratch(SCR_LN_BWD, (size_t)nblk * 2 * D);
+  if (!g_ln_partial) return 1;
   switch (D / 128) {
 #define LNB_CASE(V)                                                                                         \
   case V: {                                                                                                 \
@@ -358,8 +346,6 @@ __global__ void __launch_bounds__(256) dwconv_bwd_dw_reduce_kernel(const float* 
   else db[i - 9 * C] = t;
 }
 
-static float* g_dw_partial = nullptr;
-static size_t g_dw_partial_cap = 0;
 
 // hid [B,G,G,C] (pre-conv), dg [B,G,G,C] (grad of the GELU output) -> du_tmp (scratch, same shape), dhid, dw9 [9,C], db [C]
 int launch_dwconv_gelu_bwd(const bf16* hid, const bf16* dg, const float* w9, const float* bias, bf16* du_tmp, bf16* dhid,
@@ -378,12 +364,8 @@ int launch_dwconv_gelu_bwd(const bf16* hid, const bf16* dg, const float* w9, con
   }
   if (G == 16 && C % 64 == 0 && B <= 65535) {
     // tap / bias gradients with the tile kernel too: one [10][C] partial per image, then the fixed-order sum over images
-    const size_t need = (size_t)B * 10 * C;
-    if (need > g_dw_partial_cap) {
-      if (g_dw_partial) cudaFree(g_dw_partial);
-      TLD_CUDA_OK(cudaMalloc(&g_dw_partial, need * sizeof(float)));
-      g_dw_partial_cap = need;
-    }
+    float* g_dw_partial = device_scratch(SCR_DWCONV_DW, (size_t)B * 10 * C);
+    if (!g_dw_partial) return 1;
     if (launch_dwconv_g16_bwd(hid, du_tmp, w9, bias, reinterpret_cast<bf16*>(g_dw_partial), B, C, 3, st)) return 1;
     dwconv_bwd_dw_reduce_kernel<<<(10 * C + 255) / 256, 256, 0, st>>>(g_dw_partial, dw9, db, B, C);
     TLD_CUDA_OK(cudaGetLastError());
@@ -394,12 +376,8 @@ int launch_dwconv_gelu_bwd(const bf16* hid, const bf16* dg, const float* w9, con
   if (nchunk > 256) nchunk = 256;
   const int ppc = (int)((total + nchunk - 1) / nchunk);
   nchunk = (int)((total + ppc - 1) / ppc);
-  const size_t need = (size_t)nchunk * 10 * C;
-  if (need > g_dw_partial_cap) {
-    if (g_dw_partial) cudaFree(g_dw_partial);
-    TLD_CUDA_OK(cudaMalloc(&g_dw_partial, need * sizeof(float)));
-    g_dw_partial_cap = need;
-  }
+  float* g_dw_partial = device_scratch(SCR_DWCONV_DW, (size_t)nchunk * 10 * C);
+  if (!g_dw_partial) return 1;
   dwconv_bwd_dw_kernel<<<dim3((C / 2 + 127) / 128, nchunk), 128, 0, st>>>(hid, du_tmp, g_dw_partial, B, G, C, ppc);
   TLD_CUDA_OK(cudaGetLastError());
   dwconv_bwd_dw_reduce_kernel<<<(10 * C + 255) / 256, 256, 0, st>>>(g_dw_partial, dw9, db, nchunk, C);

@@ -137,8 +137,6 @@ __global__ void __launch_bounds__(256) transpose_f32_small_kernel(const float* _
   if (i < (long long)rows * cols) d[(size_t)(i % cols) * rows + i / cols] = s[i];
 }
 
-static float* g_split = nullptr;
-static size_t g_split_cap = 0;
 // C[M,N] (row-major) = sum_k A(i,k) B(k,j)
 static int small_gemm(const float* A, long long sa_i, long long sa_k, const float* B, long long sb_k, long long sb_j,
                       float* C, int M, int N, int K, cudaStream_t st) {
@@ -150,19 +148,14 @@ static int small_gemm(const float* A, long long sa_i, long long sa_k, const floa
   splits = (K + kps - 1) / kps;
   float* dst = C;
   if (splits > 1) {
-    const size_t need = (size_t)splits * M * N;
-    if (need > g_split_cap) {
-      if (g_split) cudaFree(g_split);
-      TLD_CUDA_OK(cudaMalloc(&g_split, need * sizeof(float)));
-      g_split_cap = need;
-    }
-    dst = g_split;
+    dst = device_scratch(SCR_SPLIT_K, (size_t)splits * M * N);
+    if (!dst) return 1;
   }
   small_gemm_kernel<<<dim3((N + 15) / 16, (M + 15) / 16, splits), 256, 0, st>>>(A, sa_i, sa_k, B, sb_k, sb_j, dst, M, N, K, kps);
   TLD_CUDA_OK(cudaGetLastError());
   if (splits > 1) {
     const long long n = (long long)M * N;
-    sum_splits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g_split, C, n, splits);
+    sum_splits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, C, n, splits);
     TLD_CUDA_OK(cudaGetLastError());
   }
   return 0;

@@ -131,9 +131,6 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict
   y[orow + 2LL * W * C8 + C8] = v;
 }
 
-static float2* g_partial = nullptr;
-static size_t g_partial_cap = 0;
-
 // out = x + h + bias[c]  (ResnetBlock2D tail: shortcut + conv2 output, with conv2's bias folded in)
 __global__ void __launch_bounds__(256) add_bias_kernel(const uint4* __restrict__ x, const uint4* __restrict__ h,
                                                        const float* __restrict__ bias, uint4* __restrict__ out,
@@ -175,11 +172,8 @@ int launch_gn_act(const bf16* x, const float* pre_bias, const float* gamma, cons
   ppb = ((ppb + pstride - 1) / pstride) * pstride;
   nblk = (HW + ppb - 1) / ppb;
   const size_t need = (size_t)B * nblk * groups;
-  if (need > g_partial_cap) {
-    if (g_partial) cudaFree(g_partial);
-    TLD_CUDA_OK(cudaMalloc(&g_partial, need * sizeof(float2)));
-    g_partial_cap = need;
-  }
+  float2* g_partial = reinterpret_cast<float2*>(device_scratch(SCR_GROUPNORM, 2 * need));
+  if (!g_partial) return 1;
   gn_stats_kernel<<<dim3(nblk, B), 256, 0, st>>>(x, pre_bias, g_partial, HW, C, groups, ppb);
   TLD_CUDA_OK(cudaGetLastError());
   gn_apply_kernel<<<dim3(nblk, B), 256, 0, st>>>(x, pre_bias, g_partial, nblk, gamma, beta, y, HW, C, groups, eps, silu, ppb);
