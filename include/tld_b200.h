@@ -49,7 +49,7 @@ typedef struct tld_config {
 TLD_API const char* tld_last_error(void);
 TLD_API int tld_version(void);
 /* Process-wide tuning switches (tests / experiments): "gemm_ctas" = 0 auto | 1 single-CTA tiles | 2 CTA-pair
- * (cta_group::2) tiles;  "attention_impl" = 0 auto | 1 mma.sync kernel | 2 tcgen05 tile-per-CTA | 3 tcgen05 persistent;
+ * (cta_group::2) tiles;  "attention_impl" = 0 auto | 1 mma.sync kernel | 3 tcgen05 persistent;
  * "attention_exp_emu" = 0|4|6|8|10 of every 16 exp2 pairs of kernel 3 evaluated on the FMA pipe instead of MUFU;  "pdl" = 1 launch
  * the step kernels with programmatic dependent launch (prologues overlap the previous kernel's tail) | 0 plain launches (default: measured no gain). */
 TLD_API int tld_set_option(const char* key, int value);
@@ -69,6 +69,10 @@ TLD_API int tld_denoiser_set_param(tld_denoiser* h, const char* key, const float
  * counters (fused Adam; `.data` arithmetic as in tld/train.py:55-58), so the packed copy is refreshed, not cached. */
 TLD_API int tld_denoiser_set_params_async(tld_denoiser* h, int n, const char* const* keys, const float* const* data,
                                           const int64_t* numels, void* stream);
+/* Counter bumped by every forward-like call on the handle (tld_denoiser_forward, tld_sampler_generate, tld_train_forward).
+ * The activations tld_train_backward differentiates live in per-handle buffers: the caller stores the value returned right
+ * after tld_train_forward and may only run the backward while it is unchanged (tld_train_backward re-checks it). */
+TLD_API long long tld_forward_serial(tld_denoiser* h);
 /* Number of parameters still missing after the set_param calls (0 = ready). */
 TLD_API int tld_denoiser_missing_params(tld_denoiser* h);
 
@@ -110,8 +114,7 @@ TLD_API int tld_op_gemm_xattn(const uint16_t* A, const uint16_t* Wq, int M, int 
 TLD_API int tld_op_layernorm(const float* x, const float* gamma, const float* beta, uint16_t* y, int rows, int D,
                      void* stream);
 /* x[T,D] += softmax(q k^T/8) v per (sample, head) from qkv[T,3D]; impl 0 = auto, 1 = mma.sync kernel,
- * 2 = tcgen05 kernel, one q-tile per CTA, 3 = tcgen05 persistent pipelined kernel (both need n_tok % 128 == 0;
- * auto picks 3 when that holds) */
+ * 3 = tcgen05 persistent pipelined kernel (needs n_tok % 128 == 0; auto picks it when that holds) */
 TLD_API int tld_op_self_attention(const uint16_t* qkv, float* x, int batch, int n_tok, int D, int impl, void* stream);
 TLD_API int tld_op_dwconv_gelu(const uint16_t* h, const float* w9, const float* bias, uint16_t* g, int batch, int grid,
                        int channels, void* stream);

@@ -211,3 +211,102 @@ def test_fused_adam_training_uses_fresh_weights():
         out = m.eval()(x.cuda(), t.cuda(), lab.cuda())
         ref = O.denoiser_forward({k: v.detach().cpu() for k, v in m.state_dict().items()}, cfg, x, t, lab)
     assert rel_fro(out, ref) < TOL
+
+
+def test_sampler_same_batch_different_steps_and_labels():
+    """ADVICE r1 (high): the captured step graph bakes in the conditioning K/V addresses.  Same batch, 30 then 15 then 20
+    steps with DIFFERENT labels each time must each follow the oracle (label rows sit in front of the per-step noise rows,
+    so nothing the graph bakes in depends on the number of steps)."""
+    from transformer_latent_diffusion_b200.diffusion import DiffusionGenerator
+
+    from oracle.ref_loader import IdentityVAE
+
+    cfg = O.OracleCfg(image_size=16, embed_dim=128, n_layers=2)
+    sd = O.synth_state_dict(cfg, 51)
+    m = _model(cfg, sd)
+    gen = DiffusionGenerator(m, IdentityVAE(), torch.device("cuda:0"), torch.float32)
+    g = torch.Generator().manual_seed(52)
+    seeds = torch.randn(3, 4, 16, 16, generator=g)
+    for n_iter in (30, 15, 20, 30):
+        labels = torch.randn(3, 768, generator=g) * 2.0
+        lat = gen.generate_latents(labels, n_iter=n_iter, num_imgs=3, img_size=16, seeds=seeds, class_guidance=5.0)
+        with torch.no_grad():
+            ref = O.generate_latents(sd, cfg, labels, seeds, n_iter=n_iter, class_guidance=5.0)
+        assert rel_fro(lat, ref) < 3 * TOL, (n_iter, rel_fro(lat, ref))
+
+
+def test_sampler_headline_config_vs_oracle():
+    """BASELINE configs[1] architecture end to end: 100M model, 256-px latent, 35-step CFG (guidance 6), B=2, against the
+    oracle's loop (VERDICT r1 weak #2: the headline sampler config had never been compared with the oracle)."""
+    from transformer_latent_diffusion_b200.diffusion import DiffusionGenerator
+
+    from oracle.ref_loader import IdentityVAE
+
+    cfg = O.OracleCfg(image_size=32, embed_dim=768, n_layers=12)
+    sd = O.synth_state_dict(cfg, 61)
+    m = _model(cfg, sd)
+    gen = DiffusionGenerator(m, IdentityVAE(), torch.device("cuda:0"), torch.float32)
+    g = torch.Generator().manual_seed(62)
+    labels = torch.randn(2, 768, generator=g)
+    seeds = torch.randn(2, 4, 32, 32, generator=g)
+    lat = gen.generate_latents(labels, n_iter=35, num_imgs=2, img_size=32, seeds=seeds, class_guidance=6.0, sharp_f=0,
+                               bright_f=0, exponent=1)
+    torch.set_num_threads(max(1, min(32, (torch.get_num_threads() or 1))))
+    with torch.no_grad():
+        ref = O.generate_latents(sd, cfg, labels, seeds, n_iter=35, class_guidance=6.0, sharp_f=0, bright_f=0, exponent=1)
+    err = rel_fro(lat, ref)
+    assert err < 2 * TOL, f"35-step CFG 100M sampler rel_fro={err:.3e}"
+
+
+@pytest.mark.parametrize("img,B", [(64, 1), (128, 1)])
+def test_forward_100m_at_512_and_1024px(img, B):
+    """BASELINE configs[2]/[4] architectures (100M model, 1024 / 4096 tokens per sample) against the oracle."""
+    cfg = O.OracleCfg(image_size=img, embed_dim=768, n_layers=12)
+    sd = O.synth_state_dict(cfg, 71)
+    g = torch.Generator().manual_seed(72)
+    x = torch.randn(B, 4, img, img, generator=g)
+    t = torch.rand(B, 1, generator=g)
+    lab = torch.randn(B, 768, generator=g)
+    with torch.no_grad():
+        ref = O.denoiser_forward(sd, cfg, x, t, lab)
+        out = _model(cfg, sd)(x.cuda(), t.cuda(), lab.cuda())
+    err = rel_fro(out, ref)
+    assert err < TOL, f"image_size={img}: rel_fro={err:.3e}"
+
+
+def test_backward_after_another_forward_is_refused():
+    """ADVICE r1 (medium): the saved activations are per handle; a backward whose forward was followed by another forward
+    (training or inference) on the same module must raise instead of silently using the wrong activations."""
+    from transformer_latent_diffusion_b200 import _lib
+
+    cfg = O.OracleCfg(image_size=16, embed_dim=128, n_layers=1)
+    m = _model(cfg, O.synth_state_dict(cfg, 81)).train()
+    g = torch.Generator().manual_seed(82)
+    x, t, lab = torch.randn(2, 4, 16, 16, generator=g).cuda(), torch.rand(2, 1, generator=g).cuda(), torch.randn(2, 768, generator=g).cuda()
+    a = m(x, t, lab)
+    b = m(x * 0.5, t, lab)
+    with pytest.raises(_lib.TldError):
+        (a.square().mean() + b.square().mean()).backward()
+    a = m(x, t, lab)
+    with torch.no_grad():
+        m(x, t, lab)           # an inference call in between clobbers the residual stream
+    with pytest.raises(_lib.TldError):
+        a.square().mean().backward()
+    a = m(x, t, lab)           # the normal pattern still works
+    a.square().mean().backward()
+    assert all(p.grad is not None for p in m.parameters())
+
+
+def test_dropout_checked_on_every_training_forward():
+    from transformer_latent_diffusion_b200 import _lib
+    from transformer_latent_diffusion_b200.denoiser import Denoiser
+
+    m = Denoiser(16, 256, 2, 128, 0.1, 1).cuda().eval()
+    x, t, lab = torch.randn(1, 4, 16, 16).cuda(), torch.rand(1, 1).cuda(), torch.randn(1, 768).cuda()
+    with torch.no_grad():
+        m(x, t, lab)            # eval-mode sampling with dropout in the config is fine (dropout is the identity)
+    m.train()
+    with pytest.raises(_lib.TldError):
+        m(x, t, lab)
+    with pytest.raises(ValueError):
+        m.eval()(x, t, lab[:, :100])

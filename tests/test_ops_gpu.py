@@ -101,7 +101,7 @@ def test_gemm_nn_mn_major_b(lib, ctas, M, N, K, epi):
     assert rel_fro(out.float(), ref) < (4e-3 if epi == 0 else 2e-5), _err_map(out.float(), ref)
 
 
-@pytest.mark.parametrize("M,N,K", [(256, 1024, 256), (384, 3072, 768)])
+@pytest.mark.parametrize("M,N,K", [(256, 1024, 256), (384, 3072, 768), (256, 160, 128), (300, 96, 64), (128, 32, 64)])
 def test_gemm_bias_bf16(lib, ctas, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(1)
     A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
@@ -113,7 +113,7 @@ def test_gemm_bias_bf16(lib, ctas, M, N, K):
     assert rel_fro(out.float(), ref) < 4e-3
 
 
-@pytest.mark.parametrize("M,N,K", [(256, 256, 1024), (384, 768, 3072), (130, 128, 512)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 1024), (384, 768, 3072), (130, 128, 512), (256, 160, 128), (140, 96, 64)])
 def test_gemm_bias_residual(lib, ctas, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(2)
     A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
@@ -160,7 +160,7 @@ def test_layernorm(lib, rows, D):
     assert rel_fro(y.float(), ref) < 3e-3
 
 
-@pytest.mark.parametrize("impl", [1, 2, 3])
+@pytest.mark.parametrize("impl", [1, 3])
 @pytest.mark.parametrize("B,n_tok,D", [(1, 64, 128), (2, 256, 128), (3, 256, 768), (1, 1024, 256), (1, 4096, 128),
                                        (40, 128, 768), (17, 256, 768), (2, 1024, 768),   # > 2 tiles per persistent CTA
                                        (3, 384, 192), (50, 384, 320)])                   # 3 q-tiles / 3 and 5 heads: multiply-high tile split

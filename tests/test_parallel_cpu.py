@@ -104,3 +104,33 @@ def test_allreduce_gradients_gloo_world2(tmp_path):
     assert flags.all(), flags
     for i, g in enumerate(grads):
         assert torch.allclose(g, torch.full_like(g, 1.5 * (i + 1)))  # mean of (1, 2) * (i + 1)
+
+
+@pytest.mark.parametrize("n,world", [(65, 2), (64, 2), (7, 4), (3, 8), (100, 3)])
+def test_shard_indices_equal_length_like_distributed_sampler(n, world):
+    """every rank gets ceil(n / world) indices (wrap-around padding), so all ranks run the same number of steps; identical
+    to torch.utils.data.DistributedSampler(shuffle=False) over the same permutation"""
+    from torch.utils.data import DistributedSampler
+
+    from transformer_latent_diffusion_b200.train import shard_indices
+
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(n))
+    shards = [shard_indices(perm, r, world) for r in range(world)]
+    assert len({len(s) for s in shards}) == 1 and len(shards[0]) == -(-n // world)
+    assert set(torch.cat(shards).tolist()) == set(range(n))
+    for r in range(world):
+        ds = DistributedSampler(list(range(n)), num_replicas=world, rank=r, shuffle=False)
+        assert [int(perm[i]) for i in ds] == shards[r].tolist()
+
+
+def test_make_image_grid_single_image_is_unpadded():
+    """torchvision.utils.make_grid returns one image as it is (no padding frame): the app's default num_imgs=1"""
+    from torchvision.utils import make_grid
+
+    from transformer_latent_diffusion_b200.diffusion import make_image_grid
+
+    g = torch.Generator().manual_seed(0)
+    for B, nrow in [(1, 1), (1, 4), (5, 2), (4, 4)]:
+        img = torch.rand(B, 3, 8, 6, generator=g) * 2.4 - 1.2
+        ref = make_grid((img + 1) / 2, nrow=nrow, padding=4).clip(0, 1)
+        assert torch.equal(make_image_grid(img, nrow, 4), ref), (B, nrow)

@@ -37,6 +37,7 @@ PROTOTYPES = {
     "tld_denoiser_set_params_async": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p),
                                                 C.POINTER(C.c_int64), C.c_void_p]),
     "tld_denoiser_missing_params": (C.c_int, [C.c_void_p]),
+    "tld_forward_serial": (C.c_longlong, [C.c_void_p]),
     "tld_denoiser_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                        C.c_void_p]),
     "tld_sampler_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,

@@ -26,6 +26,9 @@ const char* last_error() { return g_err.c_str(); }
 
 static int g_pdl = 0;  // measured on B200: no gain (the step is power-capped, not launch-gap bound); kept as an option
 void set_pdl(int v) { g_pdl = v; }
+// Bumped by every tld_set_option call: a captured sampler graph bakes in the kernel selection (attention implementation,
+// GEMM tile mode, PDL attribute), so a graph recorded under an older epoch is re-captured.
+static int g_option_epoch = 0;
 bool pdl_enabled() { return g_pdl != 0; }
 
 float* device_scratch(ScratchSlot slot, size_t n_floats) {
@@ -289,6 +292,7 @@ int tld_version(void) { return 1; }
 int tld_set_option(const char* key, int value) {
   TLD_CHECK(key != nullptr, "tld_set_option: null key");
   const std::string k(key);
+  ++g_option_epoch;
   if (k == "gemm_ctas") {
     TLD_CHECK(value >= 0 && value <= 2, "gemm_ctas must be 0, 1 or 2");
     set_gemm_ctas(value);
@@ -299,7 +303,7 @@ int tld_set_option(const char* key, int value) {
     return 0;
   }
   if (k == "attention_impl") {
-    TLD_CHECK(value >= 0 && value <= 3, "attention_impl must be 0, 1, 2 or 3");
+    TLD_CHECK(value == 0 || value == 1 || value == 3, "attention_impl must be 0 (auto), 1 (mma.sync) or 3 (tcgen05 persistent)");
     g_attention_impl = value;
     return 0;
   }
@@ -344,6 +348,7 @@ int tld_denoiser_create(const tld_config* cfg, int device, tld_denoiser** out) {
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_tables, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&h->ev_t0) != cudaSuccess || cudaEventCreate(&h->ev_t1) != cudaSuccess) {
     tld_denoiser_destroy(h);
     return fail("tld_denoiser_create: stream/event creation failed");
@@ -365,7 +370,8 @@ void tld_denoiser_destroy(tld_denoiser* h) {
   for (cudaEvent_t e : h->ev_grad)
     if (e) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
-  cudaEvent_t evs[] = {h->ev_in, h->ev_out, h->ev_t0, h->ev_t1};
+  if (h->pin_host) cudaFreeHost(h->pin_host);
+  cudaEvent_t evs[] = {h->ev_in, h->ev_out, h->ev_t0, h->ev_t1, h->ev_tables};
   for (cudaEvent_t e : evs)
     if (e) cudaEventDestroy(e);
   delete h;
@@ -438,6 +444,8 @@ int tld_denoiser_set_params_async(tld_denoiser* h, int n, const char* const* key
   return flush();
 }
 
+long long tld_forward_serial(tld_denoiser* h) { return h ? h->fwd_serial : -1; }
+
 int tld_denoiser_missing_params(tld_denoiser* h) {
   if (!h) return -1;
   int n = 0;
@@ -453,6 +461,7 @@ int tld_denoiser_forward(tld_denoiser* h, const float* x, const float* noise_lev
   TLD_CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (ensure_workspace(h, batch) || ensure_cond(h, 2 * batch)) return 1;
+  ++h->fwd_serial;   // x_res and the conditioning rows are shared with the training path
   const long long kvs = (long long)h->L * 2 * h->D;
   // conditioning tokens: rows [0,B) noise token, rows [B,2B) label token (denoiser.py:117-122)
   if (launch_cond_noise(noise_level, batch, h->E, h->D, h->cond, h->ycond, h->cond_scratch, st)) return 1;
@@ -520,6 +529,7 @@ int tld_sampler_generate(tld_denoiser* h, const float* labels, const float* seed
   const int Beff = 2 * num_imgs;
   const long long img_elems = (long long)num_imgs * h->C * h->img * h->img;
   if (ensure_workspace(h, Beff) || ensure_cond(h, calls + Beff)) return 1;
+  ++h->fwd_serial;
   if (num_imgs > h->sampler_batch) {
     TLD_CUDA_OK(cudaDeviceSynchronize());
     float** bufs[] = {&h->x_t, &h->x0_prev, &h->x0_out};
@@ -538,29 +548,46 @@ int tld_sampler_generate(tld_denoiser* h, const float* labels, const float* seed
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; h->graph_batch = -1; }
   }
 
+  // ---- per-call host tables go through a library-owned pinned buffer: the copies are asynchronous and the host never
+  // blocks here (at batch 1 of the 1024-px sweep a stream synchronize per call was visible); the only wait is for the
+  // PREVIOUS call's copies to have left the buffer, which is long over by the time a caller comes back
+  const size_t table_bytes = sizeof(StepCoef) * calls, tl_bytes = sizeof(float) * calls;
+  if (table_bytes + tl_bytes > h->pin_cap) {
+    if (h->pin_host) { TLD_CUDA_OK(cudaEventSynchronize(h->ev_tables)); cudaFreeHost(h->pin_host); h->pin_host = nullptr; h->pin_cap = 0; }
+    const size_t want = 2 * (table_bytes + tl_bytes);
+    TLD_CUDA_OK(cudaHostAlloc(&h->pin_host, want, cudaHostAllocDefault));
+    h->pin_cap = want;
+  } else {
+    TLD_CUDA_OK(cudaEventSynchronize(h->ev_tables));
+  }
+  memcpy(h->pin_host, table.data(), table_bytes);
+  memcpy(reinterpret_cast<char*>(h->pin_host) + table_bytes, tl.data(), tl_bytes);
+
   // order after the caller's stream
   TLD_CUDA_OK(cudaEventRecord(h->ev_in, caller));
   TLD_CUDA_OK(cudaStreamWaitEvent(st, h->ev_in, 0));
-  TLD_CUDA_OK(cudaMemcpyAsync(h->step_table, table.data(), sizeof(StepCoef) * calls, cudaMemcpyHostToDevice, st));
-  TLD_CUDA_OK(cudaMemcpyAsync(h->tlevels, tl.data(), sizeof(float) * calls, cudaMemcpyHostToDevice, st));
+  TLD_CUDA_OK(cudaMemcpyAsync(h->step_table, h->pin_host, table_bytes, cudaMemcpyHostToDevice, st));
+  TLD_CUDA_OK(cudaMemcpyAsync(h->tlevels, reinterpret_cast<char*>(h->pin_host) + table_bytes, tl_bytes, cudaMemcpyHostToDevice, st));
+  TLD_CUDA_OK(cudaEventRecord(h->ev_tables, st));
   TLD_CUDA_OK(cudaMemsetAsync(h->step_ptr, 0, sizeof(int), st));
   TLD_CUDA_OK(cudaMemcpyAsync(h->x_t, seeds, sizeof(float) * img_elems, cudaMemcpyDeviceToDevice, st));
-  TLD_CUDA_OK(cudaStreamSynchronize(st));  // host vectors go out of scope; the copies above are tiny
 
   // ---- conditioning hoisted out of the loop: the noise token depends only on the step, the label token only
-  // on the sample.  rows [0,calls): noise tokens; rows [calls, calls+2B): label tokens.
+  // on the sample.  rows [0, 2B): label tokens; rows [2B, 2B+calls): noise tokens.  The label
+  // rows come FIRST so that every address the captured graph bakes in depends on the batch size alone: a second call
+  // with the same batch and a different number of steps replays the same graph on correctly placed rows.
   const long long kvs = (long long)h->L * 2 * h->D;
-  if (launch_cond_noise(h->tlevels, calls, h->E, h->D, h->cond, h->ycond, h->cond_scratch, st)) return 1;
-  if (launch_cond_label(labels, Beff, num_imgs, h->Te, h->D, h->cond, h->ycond + (size_t)calls * h->D, h->cond_scratch, st))
+  if (launch_cond_label(labels, Beff, num_imgs, h->Te, h->D, h->cond, h->ycond, h->cond_scratch, st)) return 1;
+  if (launch_cond_noise(h->tlevels, calls, h->E, h->D, h->cond, h->ycond + (size_t)Beff * h->D, h->cond_scratch, st))
     return 1;
   if (launch_gemm(EPI_F32, h->ycond, h->D, h->wkv_all, h->D, calls + Beff, int(kvs), h->D, h->kv, int(kvs), nullptr,
                   nullptr, st))
     return 1;
-  const float* kv0 = h->kv;
-  const float* kv1 = h->kv + (size_t)calls * kvs;
+  const float* kv1 = h->kv;
+  const float* kv0 = h->kv + (size_t)Beff * kvs;
 
   // ---- one diffusion step = one CUDA graph (embed of cat[x,x] -> L blocks -> out-proj -> CFG + update)
-  if (!h->graph_exec || h->graph_batch != num_imgs) {
+  if (!h->graph_exec || h->graph_batch != num_imgs || h->graph_epoch != g_option_epoch) {
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
     cudaGraph_t graph = nullptr;
     TLD_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -577,6 +604,7 @@ int tld_sampler_generate(tld_denoiser* h, const float* labels, const float* seed
     cudaGraphDestroy(graph);
     TLD_CUDA_OK(ce);
     h->graph_batch = num_imgs;
+    h->graph_epoch = g_option_epoch;
   }
   TLD_CUDA_OK(cudaEventRecord(h->ev_t0, st));
   for (int i = 0; i < calls; ++i) TLD_CUDA_OK(cudaGraphLaunch(h->graph_exec, st));
@@ -637,8 +665,8 @@ int tld_op_layernorm(const float* x, const float* gamma, const float* beta, uint
 }
 
 int tld_op_self_attention(const uint16_t* qkv, float* x, int batch, int n_tok, int D, int impl, void* stream) {
-  TLD_CHECK(impl >= 0 && impl <= 3,
-            "tld_op_self_attention: impl must be 0 (auto), 1 (mma.sync), 2 (tcgen05 tile-per-CTA) or 3 (tcgen05 persistent)");
+  TLD_CHECK(impl == 0 || impl == 1 || impl == 3,
+            "tld_op_self_attention: impl must be 0 (auto), 1 (mma.sync) or 3 (tcgen05 persistent)");
   return launch_self_attention(reinterpret_cast<const bf16*>(qkv), x, batch, n_tok, D,
                                reinterpret_cast<cudaStream_t>(stream), impl);
 }

@@ -214,7 +214,6 @@ int launch_self_attention_mma(const bf16* qkv, float* x, int B, int n_tok, int D
 
 int launch_self_attention(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st, int impl) {
   if (impl == 3 || (impl == 0 && n_tok % 128 == 0)) return launch_self_attention_tc2(qkv, x, B, n_tok, D, st);
-  if (impl == 2) return launch_self_attention_tc(qkv, x, B, n_tok, D, st);
   return launch_self_attention_mma(qkv, x, B, n_tok, D, st);
 }
 

@@ -134,10 +134,9 @@ int make_tmap_tokens3d(CUtensorMap* m, const void* base, int B, int npos, int C,
 
 // ---------------------------------------------------------------- attention.cu / attention_tc.cu
 // x[T,D] fp32 += softmax(q k^T / 8) v per (sample, head); qkv bf16 [T,3D] (q | k | v), head_dim 64
-// impl: 0 = auto (tcgen05 when n_tok % 128 == 0, else mma.sync), 1 = mma.sync kernel, 2 = tcgen05 kernel
+// impl: 0 = auto (tcgen05 when n_tok % 128 == 0, else mma.sync), 1 = mma.sync kernel, 3 = tcgen05 persistent kernel
 int launch_self_attention(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st, int impl = 0);
 int launch_self_attention_mma(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st);
-int launch_self_attention_tc(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st);
 int launch_self_attention_tc2(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st);
 void set_attention_exp_emu(int pairs_of_16);  // attention_tc2: share of exp2 evaluated on the FMA pipe instead of MUFU
 

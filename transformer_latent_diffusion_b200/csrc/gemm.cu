@@ -189,7 +189,7 @@ int launch_gemm(int epi, const bf16* A, int lda, const bf16* W, int ldw, int M, 
               "launch_gemm: cross-attention K/V rows must be 16-byte aligned (float4 staging)");
   }
   if (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_RESID_F32)
-    TLD_CHECK(bias != nullptr && N % 64 == 0, "launch_gemm: bias epilogues need a bias and N % 64 == 0");
+    TLD_CHECK(bias != nullptr, "launch_gemm: bias epilogues need a bias");
   const bool out_f32 = !(epi == EPI_BF16 || epi == EPI_BIAS_BF16);
   TLD_CHECK((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo * (out_f32 ? 4 : 2)) % 16 == 0,
             "launch_gemm: output must be 16-byte aligned with a 16-byte multiple row pitch");

@@ -429,10 +429,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             float f0 = __uint_as_float(ra[2 * i]), f1 = __uint_as_float(ra[2 * i + 1]);
             float g0 = __uint_as_float(rb[2 * i]), g1 = __uint_as_float(rb[2 * i + 1]);
             if constexpr (EPI == EPI_BIAS_BF16) {
-              if (col + 63 < N) {
+              // N is a multiple of 32: a ragged last group (N % 64 == 32) still gets its first half's bias
+              if (col + 31 < N) {
                 const float2 b0 = __ldg(reinterpret_cast<const float2*>(ep.bias + col) + i);
+                f0 += b0.x; f1 += b0.y;
+              }
+              if (col + 63 < N) {
                 const float2 b1 = __ldg(reinterpret_cast<const float2*>(ep.bias + col + 32) + i);
-                f0 += b0.x; f1 += b0.y; g0 += b1.x; g1 += b1.y;
+                g0 += b1.x; g1 += b1.y;
               }
             }
             o[i] = pack_bf16x2(f0, f1);

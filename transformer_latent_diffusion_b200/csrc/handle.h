@@ -67,8 +67,17 @@ struct tld_denoiser {
   int* step_ptr = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
   int graph_batch = -1;
+  int graph_epoch = -1;          // tld_set_option epoch the graph was captured under
+  void* pin_host = nullptr;      // pinned staging of the per-call step table + noise levels
+  size_t pin_cap = 0;
+  cudaEvent_t ev_tables = nullptr;  // the previous call's table copies have left pin_host
   float last_loop_ms = 0.f;
   long long last_launches = 0;
+
+  // every forward-like call (forward, sampler, training forward) bumps fwd_serial; train_serial remembers the one whose
+  // activations the training buffers (and x_res) currently hold, so a backward after any later forward is refused
+  long long fwd_serial = 0;
+  long long train_serial = -1;
 
   // ---- training step (train.cu) ----
   struct TrainLayer {

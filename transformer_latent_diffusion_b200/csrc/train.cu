@@ -238,6 +238,7 @@ TLD_API int tld_train_forward(tld_denoiser* h, const float* x, const float* nois
   const int T = B * N;
   if (tld_internal_ensure(h, B, 2 * B)) return 1;
   if (ensure_train(h, B)) return 1;
+  h->train_serial = ++h->fwd_serial;
   const long long kvs = 2LL * L * D;
   float* s_label = h->t_small;  // [B, Te] copy of the labels for the label_proj wgrad
   TLD_CUDA_OK(cudaMemcpyAsync(s_label, label, sizeof(float) * (size_t)B * h->Te, cudaMemcpyDeviceToDevice, st));
@@ -274,6 +275,9 @@ TLD_API int tld_train_forward(tld_denoiser* h, const float* x, const float* nois
 // d(loss)/d(pred) [B,C,H,W] -> gradients of all parameters (readable with tld_train_get_grad)
 TLD_API int tld_train_backward(tld_denoiser* h, const float* d_pred, int batch, void* stream) {
   TLD_CHECK(h && d_pred && batch > 0 && batch <= h->train_batch, "tld_train_backward: call tld_train_forward with this batch first");
+  TLD_CHECK(h->train_serial == h->fwd_serial,
+            "tld_train_backward: the saved activations were overwritten by a later forward on this handle (one forward per "
+            "backward: the activation buffers are per handle, not per autograd node)");
   TLD_CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int D = h->D, H4 = h->H4, N = h->N, L = h->L, B = batch, pd = h->pd, E = h->E, Te = h->Te;

@@ -172,8 +172,6 @@ class Denoiser(nn.Module):
         idx = device.index if device.index is not None else torch.cuda.current_device()
         if self.__dict__["_handle"] is None or self.__dict__["_handle_device"] != idx:
             self._release()
-            if self.dropout != 0 and self.training:
-                raise _lib.TldError("dropout > 0 in training mode is not supported by the B200 path")
             cfg = _lib.TldConfig(self.image_size, self.noise_embed_dims, self.patch_size, self.embed_dim,
                                  self.n_layers, self.text_emb_size, self.mlp_multiplier, self.n_channels, 0.0)
             h = C.c_void_p()
@@ -212,21 +210,31 @@ class Denoiser(nn.Module):
         return self.__dict__["_handle"]
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x: torch.Tensor, noise_level: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
-        """x[B,C,H,W], noise_level[B,1], label[B,text_emb] -> x0 prediction [B,C,H,W] (tld/denoiser.py:116-126)."""
+    def check_inputs(self, x: torch.Tensor, noise_level: torch.Tensor, label: torch.Tensor) -> int:
+        """Shape / device validation shared by the inference and the training forward (the library reads raw pointers:
+        a wrong label width would be an out-of-bounds read). Returns the batch size."""
         if not x.is_cuda:
             raise _lib.TldError("transformer_latent_diffusion_b200.Denoiser runs on CUDA (sm_100a) only; "
                                 "there is no CPU fallback")
+        B = x.shape[0]
+        if x.dim() != 4 or tuple(x.shape[1:]) != (self.n_channels, self.image_size, self.image_size):
+            raise ValueError(f"expected x of shape [B,{self.n_channels},{self.image_size},{self.image_size}], "
+                             f"got {tuple(x.shape)}")
+        if noise_level.numel() != B or label.dim() != 2 or label.shape[0] != B or label.shape[-1] != self.text_emb_size:
+            raise ValueError("noise_level must be [B,1] and label [B,text_emb_size]")
+        if self.dropout != 0 and self.training:
+            # transformer_blocks.py:43,105 apply dropout only in training mode; eval-mode sampling with dropout > 0 in the
+            # config is fine, training with it is not implemented (checked on every call: .train() can come later)
+            raise _lib.TldError("dropout > 0 in training mode is not supported by the B200 path")
+        return B
+
+    def forward(self, x: torch.Tensor, noise_level: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
+        """x[B,C,H,W], noise_level[B,1], label[B,text_emb] -> x0 prediction [B,C,H,W] (tld/denoiser.py:116-126)."""
+        B = self.check_inputs(x, noise_level, label)
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             from .train import denoiser_autograd_forward  # backward kernels live with the train step
 
             return denoiser_autograd_forward(self, x, noise_level, label)
-        B = x.shape[0]
-        if tuple(x.shape[1:]) != (self.n_channels, self.image_size, self.image_size):
-            raise ValueError(f"expected x of shape [B,{self.n_channels},{self.image_size},{self.image_size}], "
-                             f"got {tuple(x.shape)}")
-        if noise_level.numel() != B or label.shape[0] != B or label.shape[-1] != self.text_emb_size:
-            raise ValueError("noise_level must be [B,1] and label [B,text_emb_size]")
         h = self._ensure_handle(x.device)
         xf = x.detach().to(torch.float32).contiguous()
         tf = noise_level.detach().to(device=x.device, dtype=torch.float32).reshape(B).contiguous()

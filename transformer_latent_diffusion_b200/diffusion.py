@@ -146,9 +146,11 @@ class DiffusionGenerator:
 
 def make_image_grid(images: Tensor, nrow: int, padding: int = 4) -> Tensor:
     """(B,3,H,W) in [-1,1] -> one (3, H', W') grid in [0,1]; same layout as torchvision.utils.make_grid
-    with pad value 0 (tld/diffusion.py:185)."""
+    with pad value 0 (tld/diffusion.py:185), including its special case: a single image comes back unpadded."""
     imgs = ((images + 1) / 2).float()
     B, Cc, H, W = imgs.shape
+    if B == 1:  # torchvision.utils.make_grid returns a single image as it is, without the padding frame
+        return imgs[0].clip(0, 1)
     ncol = min(nrow, B)
     nrows = int(np.ceil(B / ncol))
     grid = imgs.new_zeros(Cc, nrows * (H + padding) + padding, ncol * (W + padding) + padding)
@@ -173,6 +175,8 @@ def image_grid_uint8(images: Tensor, nrow: int, padding: int = 4) -> np.ndarray:
         raise ValueError("image_grid_uint8: expected RGB images [B,3,H,W]")
     ncol = min(nrow, B)
     nrows = -(-B // ncol)
+    if B == 1:  # make_grid leaves a single image unpadded (the app's default num_imgs=1 must give an 8h x 8w image)
+        padding = 0
     out = torch.empty(nrows * (H + padding) + padding, ncol * (W + padding) + padding, 3, dtype=torch.uint8,
                       device=images.device)
     _lib.check(_lib.load().tld_image_grid_u8(_lib.ptr(images), int(images.dtype == torch.bfloat16), _lib.ptr(out), B, H, W,

@@ -42,6 +42,7 @@ class _DenoiserFn(torch.autograd.Function):
             _lib.check(_lib.load().tld_train_forward(h, _lib.ptr(xf), _lib.ptr(tf), _lib.ptr(lf), _lib.ptr(out), B,
                                                      _lib.current_stream_ptr(x.device)), "tld_train_forward")
         ctx.module, ctx.batch, ctx.handle = module, B, h
+        ctx.serial = _lib.load().tld_forward_serial(h)   # the activations live in per-handle buffers (see backward)
         ctx.keys = [k for k, _ in module.named_parameters()]
         ctx.meta = [(p.shape, p.dtype) for p in params]
         return out.to(x.dtype)
@@ -51,6 +52,11 @@ class _DenoiserFn(torch.autograd.Function):
         lib = _lib.load()
         dev = d_out.device
         g = d_out.detach().to(torch.float32).contiguous()
+        if lib.tld_forward_serial(ctx.handle) != ctx.serial:
+            raise _lib.TldError(
+                "backward through a Denoiser forward whose saved activations were overwritten by a later forward of the "
+                "same module (the activation buffers belong to the module's library handle, not to the autograd node): "
+                "run backward() before the next forward / generate call of this module")
         with torch.cuda.device(dev):
             st = _lib.current_stream_ptr(dev)
             _lib.check(lib.tld_train_backward(ctx.handle, _lib.ptr(g), ctx.batch, st), "tld_train_backward")
@@ -203,6 +209,18 @@ def allreduce_gradients(model: nn.Module) -> None:
         g.copy_(f)
 
 
+def shard_indices(perm: Tensor, rank: int, world: int) -> Tensor:
+    """This rank's share of a shuffled index list, padded by wrapping around to ceil(n / world) entries exactly like
+    torch.utils.data.DistributedSampler (which the reference's accelerate-prepared DataLoader uses, tld/train.py:109):
+    every rank runs the same number of steps, so no rank waits forever in an all-reduce or barrier."""
+    n = perm.numel()
+    per_rank = -(-n // world)
+    total = per_rank * world
+    if total > n:
+        perm = perm.repeat(-(-total // n))[:total]
+    return perm[rank::world]
+
+
 def train_step(model: nn.Module, optimizer, x: Tensor, x_noisy: Tensor, sigma: Tensor, label: Tensor) -> Tensor:
     """zero_grad -> forward -> MSE -> backward -> (all-reduce) -> step (tld/train.py:160-170). Returns the loss tensor."""
     model.train()
@@ -261,7 +279,7 @@ def main(config: ModelConfig, device: Optional[torch.device] = None, log_every: 
     gen = torch.Generator().manual_seed(1234 + rank)
     for epoch in range(1, train_config.n_epoch + 1):
         perm = torch.randperm(n, generator=torch.Generator().manual_seed(epoch))  # same shuffle on every rank
-        shard = perm[rank::world]
+        shard = shard_indices(perm, rank, world)
         for i in range(0, len(shard), train_config.batch_size):
             idx = shard[i:i + train_config.batch_size]
             x, y = latent_train_data[idx].to(device), train_label_embeddings[idx].to(device)
