@@ -162,10 +162,23 @@ TLD_API int tld_train_get_grad(tld_denoiser* h, const char* key, float* dst, int
  * all kv_linear weights, range n_layers + 1 = everything else.  tld_train_wait_grad makes `stream` wait (device-side only)
  * until range `segment` of the backward enqueued last is final (segment >= n_layers: the whole backward), so the caller can
  * all-reduce block l in place on a side stream while blocks l-1..0 are still being differentiated. */
+/* Creates the gradient arena (layout only, no activations) so that tld_train_grad_layout / _offset can be queried before the
+ * first training forward: the fused optimiser lays its parameter / moment / EMA arenas out exactly like the gradients. */
+TLD_API int tld_train_prepare(tld_denoiser* h);
 TLD_API int tld_train_grad_layout(tld_denoiser* h, float** arena, int64_t* total, int64_t* out, int n_segments);
 TLD_API int tld_train_wait_grad(tld_denoiser* h, int segment, void* stream);
 /* element offset / size of the gradient of `key` inside that arena (lets the caller snapshot all gradients with one copy) */
 TLD_API int tld_train_grad_offset(tld_denoiser* h, const char* key, int64_t* offset, int64_t* numel);
+
+/* ---- optimizer.step() + update_ema (tld/train.py:170,172-173,55-58) as ONE pass over flat fp32 arenas -------------
+ * torch.optim.Adam's arithmetic (exp_avg.lerp_, exp_avg_sq.mul_.addcmul_, bias corrections 1 - beta^step as python floats,
+ * param.addcdiv_) followed by ema = alpha * ema + (1 - alpha) * param on the UPDATED parameters.  All pointers are device
+ * fp32 arrays of n elements laid out identically (the gradient arena of tld_train_grad_layout is the natural `grad`);
+ * `ema` may be NULL (ranks other than 0 keep no EMA, tld/train.py:104-106,172).  `step` is the 1-based step count,
+ * `grad_scale` multiplies the gradient first (1 = none).  weight_decay is Adam's L2 form (grad += wd * param). */
+TLD_API int tld_adam_ema_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, int64_t n,
+                              float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                              float ema_alpha, float grad_scale, void* stream);
 
 /* ---- backward-pass ops of the training step (autograd through tld/transformer_blocks.py:135-139, driven by
  * tld/train.py:160-170), exported for the parity tests (tests/test_backward_gpu.py) ------------------------------

@@ -94,3 +94,58 @@ def test_two_adam_steps_follow_oracle():
     # EMA after two updates: e2 = a^2 w0 + a(1-a) w1 + (1-a) w2  (tld/train.py:55-58)
     e = dict(ema.named_parameters())[k].detach().cpu()
     assert (e - sd[k]).abs().max() < 2.1e-3 * 6e-4 + 1e-7  # |ema - w0| <= (1-a)(|w1-w0| + |w2-w0|) ~ 1e-3 * 3 lr
+
+
+@pytest.mark.parametrize("grad_views", [False, True])
+def test_fused_adam_ema_matches_torch_adam_plus_update_ema(grad_views):
+    """tld_adam_ema_step (one kernel over flat arenas) against the reference's optimizer.step() + update_ema
+    (tld/train.py:170,172-173,55-58 = torch.optim.Adam + the EMA arithmetic) on the same gradients, three steps;
+    then the torch.optim.Adam checkpoint layout round-trips in both directions."""
+    import copy
+
+    from transformer_latent_diffusion_b200.optim import FusedAdamEMA
+    from transformer_latent_diffusion_b200.train import train_step, update_ema
+
+    cfg = O.OracleCfg(image_size=16, embed_dim=128, n_layers=2)
+    sd = O.synth_state_dict(cfg, 29)
+    ma, mb = _model(cfg, sd), _model(cfg, sd)
+    ema_a, ema_b = copy.deepcopy(ma), copy.deepcopy(mb)
+    opt_a = torch.optim.Adam(ma.parameters(), lr=1e-3)
+    opt_b = FusedAdamEMA(mb, lr=1e-3, ema_model=ema_b, alpha=0.99)
+    mb.grad_views = grad_views
+    g = torch.Generator().manual_seed(31)
+    for step in range(3):
+        x = torch.randn(4, 4, 16, 16, generator=g).cuda()
+        xn = torch.randn(4, 4, 16, 16, generator=g).cuda()
+        sg = torch.rand(4, 1, generator=g).cuda()
+        lab = torch.randn(4, 768, generator=g).cuda()
+        la = train_step(ma, opt_a, x, xn, sg, lab)
+        update_ema(ema_a, ma, 0.99)
+        lb = train_step(mb, opt_b, x, xn, sg, lab)
+        assert abs(float(la) - float(lb)) <= 1e-5 * abs(float(la)) + 1e-7, (step, float(la), float(lb))
+    for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert torch.allclose(pa, pb, rtol=1e-5, atol=2e-6), (k, float((pa - pb).abs().max()))
+    for (k, pa), (_, pb) in zip(ema_a.named_parameters(), ema_b.named_parameters()):
+        assert torch.allclose(pa, pb, rtol=1e-5, atol=2e-6), ("ema " + k, float((pa - pb).abs().max()))
+    # parameters are views of one arena laid out like the gradient arena
+    ptrs = [p.data_ptr() for p in mb.parameters()]
+    assert max(ptrs) - min(ptrs) < 4 * sum(p.numel() for p in mb.parameters()) + 4 * 1024
+    # checkpoint compatibility (tld/train.py:147 "opt_state"): fused -> torch.optim.Adam -> fused
+    sd_b = opt_b.state_dict()
+    opt_c = torch.optim.Adam(ma.parameters(), lr=1e-3)
+    opt_c.load_state_dict(sd_b)
+    sa = opt_a.state_dict()
+    for i in sa["state"]:
+        assert torch.allclose(sa["state"][i]["exp_avg"], opt_c.state_dict()["state"][i]["exp_avg"], rtol=1e-4, atol=1e-7)
+        assert float(opt_c.state_dict()["state"][i]["step"]) == 3.0
+    mc = _model(cfg, {k: v.detach().cpu() for k, v in ma.state_dict().items()})
+    opt_d = FusedAdamEMA(mc, lr=1e-3)
+    opt_d.load_state_dict(sa)
+    x = torch.randn(4, 4, 16, 16, generator=g).cuda()
+    sg = torch.rand(4, 1, generator=g).cuda()
+    lab = torch.randn(4, 768, generator=g).cuda()
+    train_step(ma, opt_a, x, x * 0.5, sg, lab)
+    train_step(mc, opt_d, x, x * 0.5, sg, lab)
+    assert opt_d.step_count == 4
+    for (k, pa), (_, pc) in zip(ma.named_parameters(), mc.named_parameters()):
+        assert torch.allclose(pa, pc, rtol=1e-5, atol=2e-6), (k, float((pa - pc).abs().max()))

@@ -389,6 +389,14 @@ TLD_API int tld_train_backward(tld_denoiser* h, const float* d_pred, int batch, 
   return 0;
 }
 
+// create the gradient arena (and its layout) without running a forward: lets an optimiser lay its flat parameter / moment
+// arenas out like the gradients before the first step
+TLD_API int tld_train_prepare(tld_denoiser* h) {
+  TLD_CHECK(h, "tld_train_prepare: null handle");
+  TLD_CUDA_OK(cudaSetDevice(h->device));
+  return ensure_train(h, 0);
+}
+
 // copy the gradient of `key` (reference state_dict key / layout) to dst (device, fp32)
 TLD_API int tld_train_get_grad(tld_denoiser* h, const char* key, float* dst, int64_t numel, void* stream) {
   TLD_CHECK(h && key && dst, "tld_train_get_grad: null argument");

@@ -61,10 +61,13 @@ class _DenoiserFn(torch.autograd.Function):
             st = _lib.current_stream_ptr(dev)
             _lib.check(lib.tld_train_backward(ctx.handle, _lib.ptr(g), ctx.batch, st), "tld_train_backward")
             ctx.module._tld_grads_allreduced = _overlapped_allreduce(ctx.module, ctx.handle, dev)
-            # ONE device copy snapshots the whole gradient arena (fresh storage per backward, so gradients that the caller
-            # keeps or accumulates never alias the library's buffers); each parameter gets a view of the snapshot
+            # Default: ONE device copy snapshots the whole gradient arena (fresh storage per backward, so gradients that the
+            # caller keeps or accumulates never alias the library's buffers); each parameter gets a view of the snapshot.
+            # With `module.grad_views = True` (set by train.main for the fused optimiser) autograd receives views of the
+            # arena itself: no 404 MB copy per step, valid until the next backward of this module - the contract of a loop
+            # that calls optimizer.zero_grad() (set_to_none) every step, as tld/train.py:164 does.
             view, offsets = _grad_arena(ctx.module, ctx.handle, dev, ctx.keys)
-            snap = view.clone()
+            snap = view if getattr(ctx.module, "grad_views", False) else view.clone()
             grads = []
             for (off, n), (shape, dtype) in zip(offsets, ctx.meta):
                 t = snap[off:off + n].view(shape)
@@ -234,13 +237,15 @@ def train_step(model: nn.Module, optimizer, x: Tensor, x_noisy: Tensor, sigma: T
 
 
 def main(config: ModelConfig, device: Optional[torch.device] = None, log_every: int = 50, vae: Optional[nn.Module] = None,
-         eval_dir: Optional[str] = None) -> nn.Module:
+         eval_dir: Optional[str] = None, fused_optimizer: bool = True) -> nn.Module:
     """Training loop with the reference's semantics (tld/train.py:62-176). Returns the EMA model (rank 0) / model.
 
     ``vae``: decoder used by the periodic ``eval_gen`` on rank 0 (the reference downloads it with
     ``AutoencoderKL.from_pretrained``, tld/train.py:78 - no network here, so the caller injects it; without one the
     evaluation images are skipped and only the checkpoint is written).  ``from_scratch=False`` resumes from
-    ``train_config.model_name`` exactly as tld/train.py:92-102 (EMA weights into the model, optimizer state, step)."""
+    ``train_config.model_name`` exactly as tld/train.py:92-102 (EMA weights into the model, optimizer state, step).
+    ``fused_optimizer``: Adam + EMA as one kernel over flat arenas (``optim.FusedAdamEMA``, same arithmetic and checkpoint
+    layout as ``torch.optim.Adam`` + ``update_ema``); False keeps the reference's two separate torch calls."""
     import os
 
     import torch.distributed as dist
@@ -260,23 +265,31 @@ def main(config: ModelConfig, device: Optional[torch.device] = None, log_every: 
         emb_val = torch.tensor(np.load(dataconfig.val_path), dtype=torch.float32).to(device)
     n = latent_train_data.shape[0]
     model = Denoiser(**asdict(denoiser_config)).to(device)
-    optimizer = torch.optim.Adam(model.parameters(), lr=train_config.lr)
     global_step = 0
+    full_state_dict = None
     if not train_config.from_scratch:  # tld/train.py:92-102 (the wandb.restore download is the caller's business)
         full_state_dict = torch.load(train_config.model_name, map_location=device)
         model.load_state_dict(full_state_dict["model_ema"])
-        optimizer.load_state_dict(full_state_dict["opt_state"])
         global_step = int(full_state_dict["global_step"])
     if world > 1:  # identical initial weights on every rank (DDP broadcasts rank 0's)
         for p in model.parameters():
             dist.broadcast(p.data, src=0)
     ema_model = copy.deepcopy(model) if rank == 0 else None
+    if fused_optimizer:
+        from .optim import FusedAdamEMA
+
+        optimizer = FusedAdamEMA(model, lr=train_config.lr, ema_model=ema_model, alpha=train_config.alpha)
+        model.grad_views = True   # the loop below zeroes the gradients every step: no snapshot copy of the arena needed
+    else:
+        optimizer = torch.optim.Adam(model.parameters(), lr=train_config.lr)
+    if full_state_dict is not None:
+        optimizer.load_state_dict(full_state_dict["opt_state"])
     diffuser = None
     if rank == 0:
         print(count_parameters(model))
         if vae is not None:
             diffuser = DiffusionGenerator(ema_model, vae, device, torch.float32)
-    gen = torch.Generator().manual_seed(1234 + rank)
+    gen = torch.Generator(device=device).manual_seed(1234 + rank)   # noise / label-dropout draws on the device (tld/train.py:128,133)
     for epoch in range(1, train_config.n_epoch + 1):
         perm = torch.randperm(n, generator=torch.Generator().manual_seed(epoch))  # same shuffle on every rank
         shard = shard_indices(perm, rank, world)
@@ -284,8 +297,8 @@ def main(config: ModelConfig, device: Optional[torch.device] = None, log_every: 
             idx = shard[i:i + train_config.batch_size]
             x, y = latent_train_data[idx].to(device), train_label_embeddings[idx].to(device)
             noise_level = torch.tensor(np.random.beta(train_config.beta_a, train_config.beta_b, len(x)), device=device)
-            noise = torch.randn(x.shape, generator=gen).to(device)
-            mask = (torch.rand(y.size(0), generator=gen) < 0.15).to(device)
+            noise = torch.randn(x.shape, generator=gen, device=device)
+            mask = torch.rand(y.size(0), generator=gen, device=device) < 0.15
             xs, x_noisy, sigma, label = noise_batch(x, y, noise_level, noise, mask, config.vae_cfg.vae_scale_factor)
             if global_step % train_config.save_and_eval_every_iters == 0:  # tld/train.py:140-158, before the step
                 if world > 1:
@@ -301,7 +314,8 @@ def main(config: ModelConfig, device: Optional[torch.device] = None, log_every: 
                                     "global_step": global_step}, train_config.model_name)
             loss = train_step(model, optimizer, xs, x_noisy, sigma, label)
             if rank == 0:
-                update_ema(ema_model, model, alpha=train_config.alpha)
+                if not fused_optimizer:   # the fused step has already folded the EMA update in
+                    update_ema(ema_model, model, alpha=train_config.alpha)
                 if global_step % log_every == 0:
                     print(f"epoch {epoch} step {global_step} train_loss {float(loss):.5f}")
             global_step += 1
