@@ -50,7 +50,8 @@ TLD_API const char* tld_last_error(void);
 TLD_API int tld_version(void);
 /* Process-wide tuning switches (tests / experiments): "gemm_ctas" = 0 auto | 1 single-CTA tiles | 2 CTA-pair
  * (cta_group::2) tiles;  "attention_impl" = 0 auto | 1 mma.sync kernel | 3 tcgen05 persistent;
- * "attention_exp_emu" = 0|4|6|8|10 of every 16 exp2 pairs of kernel 3 evaluated on the FMA pipe instead of MUFU;  "pdl" = 1 launch
+ * "attention_exp_emu" = 0|4|6|8|10 of every 16 exp2 pairs of kernel 3 evaluated on the FMA pipe instead of MUFU;  "fused_mlp" = 1 (default) up-projection + depthwise conv + GELU as one
+ * kernel for 16x16 token grids | 0 three separate kernels;  "pdl" = 1 launch
  * the step kernels with programmatic dependent launch (prologues overlap the previous kernel's tail) | 0 plain launches (default: measured no gain). */
 TLD_API int tld_set_option(const char* key, int value);
 
@@ -116,6 +117,14 @@ TLD_API int tld_op_layernorm(const float* x, const float* gamma, const float* be
 /* x[T,D] += softmax(q k^T/8) v per (sample, head) from qkv[T,3D]; impl 0 = auto, 1 = mma.sync kernel,
  * 3 = tcgen05 persistent pipelined kernel (needs n_tok % 128 == 0; auto picks it when that holds) */
 TLD_API int tld_op_self_attention(const uint16_t* qkv, float* x, int batch, int n_tok, int D, int impl, void* stream);
+/* MLPSepConv front half in one kernel for 16x16-token samples (transformer_blocks.py:95-103): out[batch*256, N] bf16 =
+ * GELU(dwconv3x3(A[batch*256, K] W[N, K]^T + col_c) + dw_b) with the hidden tensor kept on chip (CTA-pair tile = one image,
+ * halo row exchanged through distributed shared memory).  Optional LayerNorm fold: row_sums [batch*256, 2] = (sum, sum of
+ * squares) of the un-normalised fp32 rows that A is the bf16 copy of, col_s [N] = sum_k W_nk (W already scaled by gamma):
+ * value = rstd (acc - mean col_s) + col_c.  Pass NULL for both for the plain bias epilogue.  N % 256 == 0. */
+TLD_API int tld_op_gemm_up_dwconv_gelu(const uint16_t* A, const uint16_t* W, const float* col_c, const float* col_s,
+                                       const float* row_sums, const float* dw_w9, const float* dw_b, uint16_t* out, int batch,
+                                       int K, int N, void* stream);
 TLD_API int tld_op_dwconv_gelu(const uint16_t* h, const float* w9, const float* bias, uint16_t* g, int batch, int grid,
                        int channels, void* stream);
 

@@ -221,3 +221,45 @@ def test_dwconv_gelu(lib, B, grid, C):
               "dwconv")
     assert rel_fro(out.float(), ref) < 3e-3
     assert (out.float() - ref).abs().max() <= 2 ** -8 * ref.abs().max() + 1e-5
+
+
+@pytest.mark.parametrize("fold", [False, True])
+@pytest.mark.parametrize("B,K,N", [(1, 64, 256), (3, 768, 3072), (80, 128, 512), (37, 256, 1024)])
+def test_gemm_up_dwconv_gelu_fused(lib, B, K, N, fold):
+    """MLPSepConv front half in one kernel (transformer_blocks.py:95-103): up-projection (tcgen05 CTA-pair tile = one 16x16
+    image) + depthwise 3x3 + bias + GELU with the hidden tensor kept on chip; halo row exchanged between the two CTAs of a
+    pair through distributed shared memory.  80 / 37 images: several tiles per persistent CTA pair (barrier phases wrap).
+    fold: LayerNorm folded into the GEMM (gamma into the weight, mean / rstd applied on the accumulator)."""
+    g = torch.Generator(device="cuda").manual_seed(B * 31 + K)
+    M = B * 256
+    W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    bias = torch.randn(N, device="cuda", generator=g) * 0.2
+    dw = torch.randn(N, 1, 3, 3, device="cuda", generator=g) / 3
+    dwb = torch.randn(N, device="cuda", generator=g) * 0.1
+    w9 = dw.view(N, 9).t().contiguous()
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    if fold:
+        x = torch.randn(M, K, device="cuda", generator=g) * 1.7 + 0.3 * torch.randn(M, 1, device="cuda", generator=g)
+        gamma = 1 + 0.2 * torch.randn(K, device="cuda", generator=g)
+        beta = 0.1 * torch.randn(K, device="cuda", generator=g)
+        hid = torch.nn.functional.layer_norm(x, (K,), gamma, beta, 1e-5) @ W.t() + bias            # fp32 statement
+        A = x.bfloat16()
+        Wf = (W * gamma).bfloat16()
+        col_s = Wf.float().sum(1).contiguous()
+        col_c = (W @ beta + bias).contiguous()
+        sums = torch.stack([x.sum(1), (x * x).sum(1)], 1).contiguous()
+        args = (lib.ptr(A), lib.ptr(Wf), lib.ptr(col_c), lib.ptr(col_s), lib.ptr(sums))
+    else:
+        A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+        Wf = W.bfloat16()
+        hid = A.float() @ Wf.float().t() + bias
+        args = (lib.ptr(A), lib.ptr(Wf), lib.ptr(bias), None, None)
+    hid = hid.bfloat16().float().view(B, 16, 16, N)              # the kernel rounds the hidden tensor to bf16 like the 3-kernel path
+    ref = torch.nn.functional.conv2d(hid.permute(0, 3, 1, 2), dw, dwb, padding=1, groups=N)
+    ref = torch.nn.functional.gelu(ref).permute(0, 2, 3, 1).reshape(M, N)
+    lib.check(lib.load().tld_op_gemm_up_dwconv_gelu(*args, lib.ptr(w9), lib.ptr(dwb), lib.ptr(out), B, K, N, _stream()),
+              "gemm_up_dwconv_gelu")
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all(), "non-finite / unwritten outputs\n" + _err_map(out.float().nan_to_num(1e9), ref)
+    err = rel_fro(out.float(), ref)
+    assert err < (1.2e-2 if fold else 6e-3), f"rel_fro={err:.3e}\n" + _err_map(out.float(), ref)

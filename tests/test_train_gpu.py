@@ -122,11 +122,17 @@ def test_fused_adam_ema_matches_torch_adam_plus_update_ema(grad_views):
         la = train_step(ma, opt_a, x, xn, sg, lab)
         update_ema(ema_a, ma, 0.99)
         lb = train_step(mb, opt_b, x, xn, sg, lab)
-        assert abs(float(la) - float(lb)) <= 1e-5 * abs(float(la)) + 1e-7, (step, float(la), float(lb))
+        # 1-ulp differences of the fp32 weights flip bf16 roundings of the operand copies: the losses agree to ~1e-4 after
+        # the first step, not bit for bit (the arithmetic itself is pinned to 1e-6 by test_adam_ema_kernel_vs_torch)
+        assert abs(float(la) - float(lb)) <= 5e-4 * abs(float(la)) + 1e-7, (step, float(la), float(lb))
+    # Adam normalises every element's update to ~lr whatever the gradient's size, so an element whose gradient is rounding
+    # noise can move by a whole +-lr differently: compare the accumulated UPDATES in the Frobenius norm, not element-wise
     for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
-        assert torch.allclose(pa, pb, rtol=1e-5, atol=2e-6), (k, float((pa - pb).abs().max()))
+        ua, ub = pa.detach().cpu() - sd[k], pb.detach().cpu() - sd[k]
+        assert rel_fro(ub, ua) < 3e-2, (k, rel_fro(ub, ua))
     for (k, pa), (_, pb) in zip(ema_a.named_parameters(), ema_b.named_parameters()):
-        assert torch.allclose(pa, pb, rtol=1e-5, atol=2e-6), ("ema " + k, float((pa - pb).abs().max()))
+        ua, ub = pa.detach().cpu() - sd[k], pb.detach().cpu() - sd[k]
+        assert rel_fro(ub, ua) < 3e-2, ("ema " + k, rel_fro(ub, ua))
     # parameters are views of one arena laid out like the gradient arena
     ptrs = [p.data_ptr() for p in mb.parameters()]
     assert max(ptrs) - min(ptrs) < 4 * sum(p.numel() for p in mb.parameters()) + 4 * 1024
@@ -148,4 +154,37 @@ def test_fused_adam_ema_matches_torch_adam_plus_update_ema(grad_views):
     train_step(mc, opt_d, x, x * 0.5, sg, lab)
     assert opt_d.step_count == 4
     for (k, pa), (_, pc) in zip(ma.named_parameters(), mc.named_parameters()):
-        assert torch.allclose(pa, pc, rtol=1e-5, atol=2e-6), (k, float((pa - pc).abs().max()))
+        ua, uc = pa.detach().cpu() - sd[k], pc.detach().cpu() - sd[k]
+        assert rel_fro(uc, ua) < 3e-2, (k, rel_fro(uc, ua))
+
+
+@pytest.mark.parametrize("n,wd,with_ema", [(1 << 20, 0.0, True), (1000003, 0.0, False), (7, 0.01, True), (4099, 0.01, True)])
+def test_adam_ema_kernel_vs_torch(n, wd, with_ema):
+    """tld_adam_ema_step on flat arrays against torch.optim.Adam(foreach=False) + the reference's EMA arithmetic
+    (tld/train.py:55-58) fed the SAME gradients for five steps: agreement to fp32 rounding."""
+    from transformer_latent_diffusion_b200 import _lib
+
+    L = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(n)
+    p0 = torch.randn(n, device="cuda", generator=g)
+    p_ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([p_ref], lr=3e-4, weight_decay=wd, foreach=False)
+    ema_ref = p0.clone()
+    p, m, v, ema = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda"), p0.clone()
+    st = torch.cuda.current_stream().cuda_stream
+    for step in range(1, 6):
+        grad = torch.randn(n, device="cuda", generator=g) * (10.0 ** torch.randint(-4, 2, (n,), device="cuda", generator=g).float())
+        p_ref.grad = grad.clone()
+        opt.step()
+        ema_ref.mul_(0.999).add_(p_ref.detach(), alpha=1 - 0.999)
+        _lib.check(L.tld_adam_ema_step(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                       ema.data_ptr() if with_ema else None, n, 3e-4, 0.9, 0.999, 1e-8, wd, step, 0.999, 1.0, st),
+                   "tld_adam_ema_step")
+    sd = opt.state_dict()["state"][0]
+    assert torch.allclose(m, sd["exp_avg"], rtol=2e-6, atol=1e-12)
+    assert torch.allclose(v, sd["exp_avg_sq"], rtol=2e-6, atol=1e-20)
+    assert torch.allclose(p, p_ref.detach(), rtol=0, atol=2e-7 * 5), float((p - p_ref.detach()).abs().max())
+    if with_ema:
+        assert torch.allclose(ema, ema_ref, rtol=0, atol=1e-6)
+    else:
+        assert torch.equal(ema, p0)

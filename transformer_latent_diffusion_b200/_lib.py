@@ -82,6 +82,8 @@ PROTOTYPES = {
                                 C.c_int, C.c_int, C.c_void_p]),
     "tld_bwd_self_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p]),
+    "tld_op_gemm_up_dwconv_gelu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tld_op_dwconv_gelu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p]),
 }

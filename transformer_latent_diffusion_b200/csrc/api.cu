@@ -246,6 +246,10 @@ int tld_internal_ensure(tld_denoiser* h, int batch, int cond_rows) {
 namespace tld {
 
 static int g_attention_impl = 0;  // tld_set_option("attention_impl", ...)
+static int g_fused_mlp = 1;       // tld_set_option("fused_mlp", ...): up-projection + depthwise conv + GELU in one kernel
+
+// the fused MLP front half needs one CTA-pair tile per sample (16x16 token grid) and whole 256-channel tiles
+static bool use_fused_mlp(const tld_denoiser* h) { return g_fused_mlp && h->G == 16 && h->H4 % 256 == 0; }
 
 // The L decoder blocks + output projection on the tokens already in h->x_res (transformer_blocks.py:135-139).
 static int run_blocks(tld_denoiser* h, int batch, const float* kv0, long long kv0_stride, const float* kv1,
@@ -271,15 +275,20 @@ static int run_blocks(tld_denoiser* h, int batch, const float* kv0, long long kv
     if (launch_gemm(EPI_XATTN_RESID_F32, h->xn, D, ly.wq, D, T, D, D, h->x_res, D, nullptr, &xa, st)) return 1;
     // x = MLPSepConv(LN3(x)) + x
     if (launch_layernorm_bf16(h->x_res, ly.ln3w, ly.ln3b, h->xn, T, D, st)) return 1;
-    if (launch_gemm(EPI_BIAS_BF16, h->xn, D, ly.wup, D, T, H4, D, h->hid, H4, ly.bup, nullptr, st)) return 1;
-    if (launch_dwconv_gelu(h->hid, ly.dww9, ly.dwb, h->hid2, batch, h->G, H4, st)) return 1;
+    if (use_fused_mlp(h)) {
+      if (launch_gemm_up_dwconv_gelu(h->xn, D, ly.wup, D, T, H4, D, ly.bup, nullptr, nullptr, 1e-5f, ly.dww9, ly.dwb, h->hid2, st))
+        return 1;
+    } else {
+      if (launch_gemm(EPI_BIAS_BF16, h->xn, D, ly.wup, D, T, H4, D, h->hid, H4, ly.bup, nullptr, st)) return 1;
+      if (launch_dwconv_gelu(h->hid, ly.dww9, ly.dwb, h->hid2, batch, h->G, H4, st)) return 1;
+    }
     if (launch_gemm(EPI_BIAS_RESID_F32, h->hid2, H4, ly.wdown, H4, T, D, H4, h->x_res, D, ly.bdown, nullptr, st))
       return 1;
   }
   return launch_outproj(h->x_res, h->out_w, h->out_b, out, batch, h->C, h->img, h->patch, D, st);
 }
 
-static int kernels_per_forward(const tld_denoiser* h) { return 1 + 9 * h->L + 1; }
+static int kernels_per_forward(const tld_denoiser* h) { return 1 + (use_fused_mlp(h) ? 8 : 9) * h->L + 1; }
 
 }  // namespace tld
 
@@ -305,6 +314,10 @@ int tld_set_option(const char* key, int value) {
   if (k == "attention_impl") {
     TLD_CHECK(value == 0 || value == 1 || value == 3, "attention_impl must be 0 (auto), 1 (mma.sync) or 3 (tcgen05 persistent)");
     g_attention_impl = value;
+    return 0;
+  }
+  if (k == "fused_mlp") {
+    g_fused_mlp = value != 0;
     return 0;
   }
   if (k == "attention_exp_emu") {
@@ -669,6 +682,14 @@ int tld_op_self_attention(const uint16_t* qkv, float* x, int batch, int n_tok, i
             "tld_op_self_attention: impl must be 0 (auto), 1 (mma.sync) or 3 (tcgen05 persistent)");
   return launch_self_attention(reinterpret_cast<const bf16*>(qkv), x, batch, n_tok, D,
                                reinterpret_cast<cudaStream_t>(stream), impl);
+}
+
+int tld_op_gemm_up_dwconv_gelu(const uint16_t* A, const uint16_t* W, const float* col_c, const float* col_s,
+                               const float* row_sums, const float* dw_w9, const float* dw_b, uint16_t* out, int batch, int K,
+                               int N, void* stream) {
+  return launch_gemm_up_dwconv_gelu(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(W), K, batch * 256, N, K,
+                                    col_c, col_s, row_sums, 1e-5f, dw_w9, dw_b, reinterpret_cast<bf16*>(out),
+                                    reinterpret_cast<cudaStream_t>(stream));
 }
 
 int tld_op_dwconv_gelu(const uint16_t* hsrc, const float* w9, const float* bias, uint16_t* g, int batch, int grid,

@@ -4,6 +4,7 @@
 #include <math.h>
 
 #include "common.h"
+#include "dwconv_math.cuh"
 #include "launch.h"
 #include "ptx.cuh"
 
@@ -390,35 +391,6 @@ __global__ void __launch_bounds__(256) dwconv_gelu_generic_kernel(const bf16* __
       }
     }
   }
-}
-
-// packed-fp32 (FFMA2) helpers ffma2()/fmul2() live in ptx.cuh
-__device__ __forceinline__ float2 unpack_bf16x2(uint32_t w) {
-  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// erf-GELU on a channel pair, MUFU-free: erf(v/sqrt2) = v R(v^2) with R a degree-7 minimax polynomial on |v| <= 3.96
-// (|erf err| <= 4.4e-5; beyond 3.96 the argument is clamped, erf -> 0.99988 instead of 1: |gelu err| <= 3e-4 out there and
-// <= 9e-5 inside - the bf16 rounding of the result is 2^-9 relative).  All of it is packed FFMA2 on the FMA pipe: the
-// Abramowitz-Stegun form needs a reciprocal and an exponential per element, and MUFU issues only 16 results/clk/SM.
-__device__ __forceinline__ float2 gelu2(float2 v) {
-  const float2 vc = make_float2(fminf(fmaxf(v.x, -3.96f), 3.96f), fminf(fmaxf(v.y, -3.96f), 3.96f));
-  const float2 u = fmul2(vc, vc);
-  float2 r = ffma2(make_float2(-3.3440241686832906e-09f, -3.3440241686832906e-09f), u,
-                   make_float2(2.5340079901070567e-07f, 2.5340079901070567e-07f));
-  r = ffma2(r, u, make_float2(-8.418431207246613e-06f, -8.418431207246613e-06f));
-  r = ffma2(r, u, make_float2(0.00016371029778383672f, 0.00016371029778383672f));
-  r = ffma2(r, u, make_float2(-0.002110206289216876f, -0.002110206289216876f));
-  r = ffma2(r, u, make_float2(0.019370341673493385f, 0.019370341673493385f));
-  r = ffma2(r, u, make_float2(-0.13240252435207367f, -0.13240252435207367f));
-  r = ffma2(r, u, make_float2(0.7977136969566345f, 0.7977136969566345f));
-  const float2 e = fmul2(vc, r);                                   // erf(v / sqrt 2)
-  const float2 hv = fmul2(v, make_float2(0.5f, 0.5f));
-  return ffma2(hv, e, hv);                                         // v/2 (1 + erf)
 }
 
 // d/dv gelu(v) = Phi(v) + v phi(v) on a channel pair (training backward): Phi through the same erf polynomial,
