@@ -51,7 +51,8 @@ TLD_API int tld_version(void);
 /* Process-wide tuning switches (tests / experiments): "gemm_ctas" = 0 auto | 1 single-CTA tiles | 2 CTA-pair
  * (cta_group::2) tiles;  "attention_impl" = 0 auto | 1 mma.sync kernel | 3 tcgen05 persistent;
  * "attention_exp_emu" = 0|4|6|8|10 of every 16 exp2 pairs of kernel 3 evaluated on the FMA pipe instead of MUFU;  "fused_mlp" = 1 (default) up-projection + depthwise conv + GELU as one
- * kernel for 16x16 token grids | 0 three separate kernels;  "pdl" = 1 launch
+ * kernel for 16x16 token grids | 0 three separate kernels;  "ln_fold" = 1 norm1 / norm3 folded into the neighbouring GEMMs (their
+ * statistics ride on the residual epilogues; measured slower on B200, see csrc/api.cu) | 0 (default) separate LayerNorm kernels;  "pdl" = 1 launch
  * the step kernels with programmatic dependent launch (prologues overlap the previous kernel's tail) | 0 plain launches (default: measured no gain). */
 TLD_API int tld_set_option(const char* key, int value);
 
@@ -112,6 +113,22 @@ TLD_API int tld_op_gemm_nn(int epi, const uint16_t* A, const uint16_t* B, int M,
  * x[M,D] += softmax2(q k0, q k1)(v0,v1) with q = A Wq^T; kv0/kv1 [rows, 2D] fp32 (K | V). */
 TLD_API int tld_op_gemm_xattn(const uint16_t* A, const uint16_t* Wq, int M, int D, float* x, const float* kv0,
                       const float* kv1, int n_tok, void* stream);
+/* LayerNorm folding (norm1 -> qkv_linear, norm3 -> mlp.0; transformer_blocks.py:136,138): the LayerNorm kernels disappear.
+ * Consumer: out_bf16[M,N] = rstd_r (A Wf^T - mean_r col_s) + col_c with A = bf16 of the UN-normalised rows, Wf = bf16(gamma (.) W),
+ * col_s[n] = sum_k Wf[n,k], col_c[n] = sum_k beta[k] W[n,k] (+ bias); mean_r / rstd_r from row_part [M, n_part] partial (sum, sum of
+ * squares) of the fp32 rows (n_part = K/32, fixed summation order: deterministic). */
+TLD_API int tld_op_gemm_lnfold(const uint16_t* A, const uint16_t* Wf, int M, int N, int K, uint16_t* out, const float* col_c,
+                               const float* col_s, const float* row_part, int n_part, void* stream);
+/* Producers: x_f32[M,N] = x + A W^T + bias written back explicitly, plus xb_out = bf16(x_new) and part_out [M, N/32] = per-32-column
+ * (sum, sum of squares) of the new rows - what the consumer above needs; the cross-attention variant adds the 2-key SDPA instead. */
+TLD_API int tld_op_gemm_bias_resid_lnp(const uint16_t* A, const uint16_t* W, int M, int N, int K, float* x, const float* bias,
+                                       uint16_t* xb_out, float* part_out, void* stream);
+TLD_API int tld_op_gemm_xattn_lnp(const uint16_t* A, const uint16_t* Wq, int M, int D, float* x, const float* kv0,
+                                  const float* kv1, int n_tok, uint16_t* xb_out, float* part_out, void* stream);
+/* fp32 rows -> bf16 copy + [rows, D/32] partials (the patch embedding's rows); gamma-folded weight + its column constants */
+TLD_API int tld_op_rowstats_cast(const float* x, uint16_t* xb, float* part, int rows, int D, void* stream);
+TLD_API int tld_op_ln_fold_weights(const float* W, const float* gamma, const float* beta, const float* bias, uint16_t* Wf,
+                                   float* s, float* c, int N, int K, void* stream);
 TLD_API int tld_op_layernorm(const float* x, const float* gamma, const float* beta, uint16_t* y, int rows, int D,
                      void* stream);
 /* x[T,D] += softmax(q k^T/8) v per (sample, head) from qkv[T,3D]; impl 0 = auto, 1 = mma.sync kernel,

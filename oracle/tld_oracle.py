@@ -313,7 +313,7 @@ def generate_latents(sd, cfg: OracleCfg, labels: torch.Tensor, seeds: torch.Tens
     f = model if model is not None else (lambda x, t, l: denoiser_forward(sd, cfg, x, t, l))
 
     def pred(xt, s):  # diffusion.py:94-103
-        t = torch.full((2 * num, 1), s, dtype=xt.dtype)
+        t = torch.full((2 * num, 1), s, dtype=xt.dtype, device=xt.device)
         x0 = cfg_combine(f(torch.cat([xt, xt]), t, lab2), num, class_guidance)
         if trace is not None:
             trace.append((xt.clone(), s, x0.clone()))

@@ -153,6 +153,8 @@ def test_sampler_repeatable_and_stats():
             ref = O.generate_latents(sd, cfg, labels, seeds, n_iter=n_iter, exponent=exponent)
         assert rel_fro(a, ref) < 3 * TOL, (n_iter, exponent, rel_fro(a, ref))
     ms, launches = gen.last_stats()
+    # per step: embed + 9 kernels per block (8x8 token grid: no fused MLP) + out-projection + CFG update + step counter;
+    # 3 prologue launches
     assert ms > 0 and launches == 50 * (9 * 1 + 4) + 3
 
 
@@ -310,3 +312,31 @@ def test_dropout_checked_on_every_training_forward():
         m(x, t, lab)
     with pytest.raises(ValueError):
         m.eval()(x, t, lab[:, :100])
+
+
+@pytest.mark.parametrize("img,D,L,B", [(32, 768, 2, 3), (16, 256, 2, 5), (64, 128, 1, 1)])
+def test_forward_with_layernorm_fold_option(img, D, L, B):
+    """tld_set_option("ln_fold", 1): norm1 / norm3 folded into qkv_linear / mlp.0 (gamma into the weights, mean / rstd on the
+    accumulator from row statistics that the residual epilogues emit).  Off by default (slower on B200), kept parity-tested."""
+    from transformer_latent_diffusion_b200 import _lib
+
+    cfg = O.OracleCfg(image_size=img, embed_dim=D, n_layers=L)
+    sd = O.synth_state_dict(cfg, 91)
+    g = torch.Generator().manual_seed(92)
+    sd = {k: (v + 0.1 * torch.randn(v.shape, generator=g) if k.endswith(("norm1.weight", "norm1.bias", "norm3.weight", "norm3.bias")) else v)
+          for k, v in sd.items()}     # non-trivial gamma / beta
+    x = torch.randn(B, 4, img, img, generator=g)
+    t = torch.rand(B, 1, generator=g)
+    lab = torch.randn(B, 768, generator=g)
+    with torch.no_grad():
+        ref = O.denoiser_forward(sd, cfg, x, t, lab)
+    m = _model(cfg, sd)
+    _lib.check(_lib.load().tld_set_option(b"ln_fold", 1), "opt")
+    try:
+        with torch.no_grad():
+            out = m(x.cuda(), t.cuda(), lab.cuda())
+            out2 = m(x.cuda(), t.cuda(), lab.cuda())
+    finally:
+        _lib.check(_lib.load().tld_set_option(b"ln_fold", 0), "opt")
+    assert torch.equal(out, out2)          # partial statistics are summed in a fixed order: deterministic
+    assert rel_fro(out, ref) < TOL, f"rel_fro={rel_fro(out, ref):.3e}"

@@ -263,3 +263,89 @@ def test_gemm_up_dwconv_gelu_fused(lib, B, K, N, fold):
     assert torch.isfinite(out.float()).all(), "non-finite / unwritten outputs\n" + _err_map(out.float().nan_to_num(1e9), ref)
     err = rel_fro(out.float(), ref)
     assert err < (1.2e-2 if fold else 6e-3), f"rel_fro={err:.3e}\n" + _err_map(out.float(), ref)
+
+
+def _row_partials(x):
+    M, D = x.shape
+    g = x.view(M, D // 32, 32)
+    return torch.stack([g.sum(-1), (g * g).sum(-1)], -1).contiguous()     # [M, D/32, 2]
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 2304, 768), (4096, 768, 256), (300, 192, 128), (8192, 3072, 768)])
+def test_gemm_layernorm_fold_consumer(lib, ctas, M, N, K):
+    """norm1 / norm3 folded into the following GEMM: weights from tld_op_ln_fold_weights, row partials from
+    tld_op_rowstats_cast, against LayerNorm(x) W^T + bias in fp32."""
+    L = lib.load()
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    x = torch.randn(M, K, device="cuda", generator=g) * 1.5 + 0.4 * torch.randn(M, 1, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    gamma = 1 + 0.3 * torch.randn(K, device="cuda", generator=g)
+    beta = 0.2 * torch.randn(K, device="cuda", generator=g)
+    bias = 0.3 * torch.randn(N, device="cuda", generator=g)
+    ref = torch.nn.functional.layer_norm(x, (K,), gamma, beta, 1e-5) @ W.t() + bias
+    Wf = torch.empty(N, K, device="cuda", dtype=torch.bfloat16)
+    s, c = torch.empty(N, device="cuda"), torch.empty(N, device="cuda")
+    lib.check(L.tld_op_ln_fold_weights(lib.ptr(W), lib.ptr(gamma), lib.ptr(beta), lib.ptr(bias), lib.ptr(Wf), lib.ptr(s), lib.ptr(c),
+                                       N, K, _stream()), "fold")
+    assert torch.equal(Wf, (W * gamma).bfloat16())
+    assert torch.allclose(s, Wf.float().sum(1), rtol=1e-5, atol=1e-5) and torch.allclose(c, W @ beta + bias, rtol=1e-4, atol=1e-5)
+    xb = torch.empty(M, K, device="cuda", dtype=torch.bfloat16)
+    part = torch.empty(M, K // 32, 2, device="cuda")
+    if K % 128 == 0:
+        lib.check(L.tld_op_rowstats_cast(lib.ptr(x), lib.ptr(xb), lib.ptr(part), M, K, _stream()), "rowstats")
+        assert torch.equal(xb, x.bfloat16())
+        assert torch.allclose(part, _row_partials(x), rtol=1e-5, atol=1e-5)
+    else:
+        xb, part = x.bfloat16(), _row_partials(x)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    lib.check(L.tld_op_gemm_lnfold(lib.ptr(xb), lib.ptr(Wf), M, N, K, lib.ptr(out), lib.ptr(c), lib.ptr(s), lib.ptr(part), K // 32,
+                                   _stream()), "gemm_lnfold")
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert rel_fro(out.float(), ref) < 8e-3, _err_map(out.float(), ref)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 768, 3072), (4096, 256, 1024), (300, 192, 128), (8192, 768, 512)])
+def test_gemm_bias_residual_producer(lib, ctas, M, N, K):
+    """mlp.3 + residual with the explicit read-modify-write epilogue that also emits bf16(x_new) and the per-32-column row
+    statistics of x_new (the inputs of the next block's folded norm1)."""
+    g = torch.Generator(device="cuda").manual_seed(M * 3 + N)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    x = torch.randn(M, N, device="cuda", generator=g)
+    ref = x + A.float() @ W.float().t() + bias
+    xb = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    part = torch.full((M, N // 32, 2), float("nan"), device="cuda")
+    lib.check(lib.load().tld_op_gemm_bias_resid_lnp(lib.ptr(A), lib.ptr(W), M, N, K, lib.ptr(x), lib.ptr(bias), lib.ptr(xb),
+                                                    lib.ptr(part), _stream()), "gemm_lnp")
+    torch.cuda.synchronize()
+    assert rel_fro(x, ref) < 2e-5, _err_map(x, ref)
+    assert torch.equal(xb, x.bfloat16())                       # the bf16 copy is the rounding of exactly what was stored
+    assert torch.allclose(part, _row_partials(x), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("B,n_tok,D", [(2, 64, 128), (3, 256, 768), (16, 256, 768), (1, 1024, 256)])
+def test_gemm_cross_attention_producer(lib, ctas, B, n_tok, D):
+    """q_linear + 2-key SDPA + residual as an explicit read-modify-write that also emits bf16(x_new) + row partials"""
+    g = torch.Generator(device="cuda").manual_seed(13)
+    M = B * n_tok
+    A = torch.randn(M, D, device="cuda", generator=g).bfloat16()
+    Wq = (torch.randn(D, D, device="cuda", generator=g) / math.sqrt(D)).bfloat16()
+    kv0 = torch.randn(B, 2 * D, device="cuda", generator=g)
+    kv1 = torch.randn(B, 2 * D, device="cuda", generator=g)
+    x = torch.randn(M, D, device="cuda", generator=g)
+    H = D // 64
+    q = (A.float() @ Wq.float().t()).view(B, n_tok, H, 64)
+    k = torch.stack([kv0[:, :D], kv1[:, :D]], 1).view(B, 2, H, 64)
+    v = torch.stack([kv0[:, D:], kv1[:, D:]], 1).view(B, 2, H, 64)
+    sc = torch.einsum("bnhd,bshd->bhns", q, k) / 8.0
+    ref = x + torch.einsum("bhns,bshd->bnhd", torch.softmax(sc, -1), v).reshape(M, D)
+    xb = torch.full((M, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    part = torch.full((M, D // 32, 2), float("nan"), device="cuda")
+    lib.check(lib.load().tld_op_gemm_xattn_lnp(lib.ptr(A), lib.ptr(Wq), M, D, lib.ptr(x), lib.ptr(kv0), lib.ptr(kv1), n_tok,
+                                               lib.ptr(xb), lib.ptr(part), _stream()), "gemm_xattn_lnp")
+    torch.cuda.synchronize()
+    assert rel_fro(x, ref) < 1e-4, _err_map(x, ref)
+    assert torch.equal(xb, x.bfloat16())
+    assert torch.allclose(part, _row_partials(x), rtol=1e-4, atol=1e-4)

@@ -118,7 +118,9 @@ static int dev_alloc(tld_denoiser* h, T** p, long long n, bool track = true) {
 
 static int add_slot(tld_denoiser* h, const std::string& key, PackKind kind, void* dst, long long numel, int rows = 0,
                     int cols = 0) {
-  h->slots[key] = Slot{kind, dst, numel, rows, cols, false};
+  Slot s{};
+  s.kind = kind; s.dst = dst; s.numel = numel; s.rows = rows; s.cols = cols; s.filled = false;
+  h->slots[key] = s;
   return 0;
 }
 
@@ -162,13 +164,23 @@ static int build_params(tld_denoiser* h) {
   }
   if (dev_alloc(h, &h->wkv_all, (long long)L * 2 * D * D)) return 1;
   h->layers.resize(L);
+  h->fold.resize(L);
   for (int l = 0; l < L; ++l) {
     auto& ly = h->layers[l];
     const std::string b = tb + "decoder_blocks." + std::to_string(l) + ".";
     if (alloc_slot(h, b + "self_attention.qkv_linear.weight", P_BF16, &ly.wqkv, 3LL * D * D)) return 1;
+    {
+      auto& fl = h->fold[l];
+      if (dev_alloc(h, &fl.wqkv32, 3LL * D * D) || dev_alloc(h, &fl.wup32, (long long)H4 * D) || dev_alloc(h, &fl.wqkv_f, 3LL * D * D) ||
+          dev_alloc(h, &fl.wup_f, (long long)H4 * D) || dev_alloc(h, &fl.s_qkv, 3LL * D) || dev_alloc(h, &fl.c_qkv, 3LL * D) ||
+          dev_alloc(h, &fl.s_up, H4) || dev_alloc(h, &fl.c_up, H4))
+        return 1;
+      h->slots[b + "self_attention.qkv_linear.weight"].shadow = fl.wqkv32;
+    }
     if (alloc_slot(h, b + "cross_attention.q_linear.weight", P_BF16, &ly.wq, (long long)D * D)) return 1;
     add_slot(h, b + "cross_attention.kv_linear.weight", P_BF16, h->wkv_all + (size_t)l * 2 * D * D, 2LL * D * D);
     if (alloc_slot(h, b + "mlp.mlp.0.weight", P_BF16, &ly.wup, (long long)H4 * D)) return 1;
+    h->slots[b + "mlp.mlp.0.weight"].shadow = h->fold[l].wup32;
     if (alloc_slot(h, b + "mlp.mlp.3.weight", P_BF16, &ly.wdown, (long long)D * H4)) return 1;
     F32(b + "mlp.mlp.0.bias", ly.bup, H4)
     F32(b + "mlp.mlp.1.bias", ly.dwb, H4)
@@ -190,10 +202,11 @@ static int build_params(tld_denoiser* h) {
 }
 
 static void free_workspace(tld_denoiser* h) {
-  void* ptrs[] = {h->x_res, h->xn, h->qkv, h->hid, h->hid2, h->model_out};
+  void* ptrs[] = {h->x_res, h->xn, h->qkv, h->hid, h->hid2, h->model_out, h->xb[0], h->xb[1], h->part[0], h->part[1]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   h->x_res = nullptr; h->xn = nullptr; h->qkv = nullptr; h->hid = nullptr; h->hid2 = nullptr; h->model_out = nullptr;
+  h->xb[0] = h->xb[1] = nullptr; h->part[0] = h->part[1] = nullptr;
   h->ws_batch = 0;
   if (h->graph_exec) {
     cudaGraphExecDestroy(h->graph_exec);
@@ -213,6 +226,10 @@ static int ensure_workspace(tld_denoiser* h, int batch) {
   if (dev_alloc(h, &h->hid, T * h->H4, false)) return 1;
   if (dev_alloc(h, &h->hid2, T * h->H4, false)) return 1;
   if (dev_alloc(h, &h->model_out, (long long)batch * h->C * h->img * h->img, false)) return 1;
+  for (int i = 0; i < 2; ++i) {
+    if (dev_alloc(h, &h->xb[i], T * h->D, false)) return 1;
+    if (dev_alloc(h, &h->part[i], T * (h->D / 32), false)) return 1;
+  }
   h->ws_batch = batch;
   return 0;
 }
@@ -247,6 +264,28 @@ namespace tld {
 
 static int g_attention_impl = 0;  // tld_set_option("attention_impl", ...)
 static int g_fused_mlp = 1;       // tld_set_option("fused_mlp", ...): up-projection + depthwise conv + GELU in one kernel
+// tld_set_option("ln_fold", ...): norm1 / norm3 folded into the neighbouring GEMMs.  OFF by default: measured on B200 the
+// explicit read-modify-write epilogues cost more than the two LayerNorm kernels they remove (per layer: mlp.3 105.7 -> 129 us,
+// cross-attention 42.5 -> 66 us, qkv 81 -> 90 us against 2 x 23.7 us saved; 256-px step 7.31 -> 7.49 ms).  The TMA reduce-add
+// residual is a read-modify-write AT L2 with deep queues; doing it in the SM needs x_old in shared memory several chunks
+// ahead, and the 6-stage operand pipeline leaves no room for that.  Kept selectable and parity-tested.
+static int g_ln_fold = 0;
+
+static bool use_ln_fold(const tld_denoiser* h) { return g_ln_fold && h->D % 128 == 0; }
+
+// W' = bf16(gamma (.) W), s, c of every layer from the fp32 shadows, once after each parameter refresh
+static int ensure_fold(tld_denoiser* h, cudaStream_t st) {
+  if (!h->fold_dirty) return 0;
+  const int D = h->D, H4 = h->H4;
+  for (int l = 0; l < h->L; ++l) {
+    const auto& ly = h->layers[l];
+    const auto& fl = h->fold[l];
+    if (launch_ln_fold_weights(fl.wqkv32, ly.ln1w, ly.ln1b, nullptr, fl.wqkv_f, fl.s_qkv, fl.c_qkv, 3 * D, D, st)) return 1;
+    if (launch_ln_fold_weights(fl.wup32, ly.ln3w, ly.ln3b, ly.bup, fl.wup_f, fl.s_up, fl.c_up, H4, D, st)) return 1;
+  }
+  h->fold_dirty = false;
+  return 0;
+}
 
 // the fused MLP front half needs one CTA-pair tile per sample (16x16 token grid) and whole 256-channel tiles
 static bool use_fused_mlp(const tld_denoiser* h) { return g_fused_mlp && h->G == 16 && h->H4 % 256 == 0; }
@@ -256,11 +295,21 @@ static int run_blocks(tld_denoiser* h, int batch, const float* kv0, long long kv
                       long long kv1_stride, const int* step_ptr, float* out, cudaStream_t st) {
   const int D = h->D, H4 = h->H4, N = h->N;
   const int T = batch * N;
+  const bool fold = use_ln_fold(h);
+  const int n_part = D / 32;
+  int cur = 0;   // which xb / part buffer holds the current residual rows
+  if (fold && launch_rowstats_cast(h->x_res, h->xb[0], h->part[0], T, D, st)) return 1;   // the embedding's rows
   for (int l = 0; l < h->L; ++l) {
     const auto& ly = h->layers[l];
+    const auto& fl = h->fold[l];
     // x = SelfAttention(LN1(x)) + x
-    if (launch_layernorm_bf16(h->x_res, ly.ln1w, ly.ln1b, h->xn, T, D, st)) return 1;
-    if (launch_gemm(EPI_BF16, h->xn, D, ly.wqkv, D, T, 3 * D, D, h->qkv, 3 * D, nullptr, nullptr, st)) return 1;
+    if (fold) {   // norm1 folded: A = bf16(x), W = gamma (.) Wqkv, mean / rstd applied on the accumulator
+      LnFoldArgs ln{fl.s_qkv, h->part[cur], n_part, 1e-5f, nullptr, 0, nullptr};
+      if (launch_gemm(EPI_LNFOLD_BF16, h->xb[cur], D, fl.wqkv_f, D, T, 3 * D, D, h->qkv, 3 * D, fl.c_qkv, nullptr, st, &ln)) return 1;
+    } else {
+      if (launch_layernorm_bf16(h->x_res, ly.ln1w, ly.ln1b, h->xn, T, D, st)) return 1;
+      if (launch_gemm(EPI_BF16, h->xn, D, ly.wqkv, D, T, 3 * D, D, h->qkv, 3 * D, nullptr, nullptr, st)) return 1;
+    }
     if (launch_self_attention(h->qkv, h->x_res, batch, N, D, st, g_attention_impl)) return 1;
     // x = CrossAttention(LN2(x), y) + x
     if (launch_layernorm_bf16(h->x_res, ly.ln2w, ly.ln2b, h->xn, T, D, st)) return 1;
@@ -272,23 +321,45 @@ static int run_blocks(tld_denoiser* h, int batch, const float* kv0, long long kv
     xa.step_ptr = step_ptr;
     xa.n_tok = N;
     xa.embed_dim = D;
-    if (launch_gemm(EPI_XATTN_RESID_F32, h->xn, D, ly.wq, D, T, D, D, h->x_res, D, nullptr, &xa, st)) return 1;
+    if (fold) {   // producer of norm3's inputs: new rows also as bf16 + their statistics partials
+      LnFoldArgs ln{nullptr, nullptr, 0, 1e-5f, h->xb[cur ^ 1], D, h->part[cur ^ 1]};
+      if (launch_gemm(EPI_XATTN_RESID_LNP, h->xn, D, ly.wq, D, T, D, D, h->x_res, D, nullptr, &xa, st, &ln)) return 1;
+      cur ^= 1;
+    } else {
+      if (launch_gemm(EPI_XATTN_RESID_F32, h->xn, D, ly.wq, D, T, D, D, h->x_res, D, nullptr, &xa, st)) return 1;
+    }
     // x = MLPSepConv(LN3(x)) + x
-    if (launch_layernorm_bf16(h->x_res, ly.ln3w, ly.ln3b, h->xn, T, D, st)) return 1;
+    const bf16* a_up = h->xn;
+    if (fold) a_up = h->xb[cur];
+    else if (launch_layernorm_bf16(h->x_res, ly.ln3w, ly.ln3b, h->xn, T, D, st)) return 1;
     if (use_fused_mlp(h)) {
-      if (launch_gemm_up_dwconv_gelu(h->xn, D, ly.wup, D, T, H4, D, ly.bup, nullptr, nullptr, 1e-5f, ly.dww9, ly.dwb, h->hid2, st))
+      if (launch_gemm_up_dwconv_gelu(a_up, D, fold ? fl.wup_f : ly.wup, D, T, H4, D, fold ? fl.c_up : ly.bup, fold ? fl.s_up : nullptr,
+                                     fold ? h->part[cur] : nullptr, fold ? n_part : 0, 1e-5f, ly.dww9, ly.dwb, h->hid2, st))
         return 1;
     } else {
-      if (launch_gemm(EPI_BIAS_BF16, h->xn, D, ly.wup, D, T, H4, D, h->hid, H4, ly.bup, nullptr, st)) return 1;
+      if (fold) {
+        LnFoldArgs ln{fl.s_up, h->part[cur], n_part, 1e-5f, nullptr, 0, nullptr};
+        if (launch_gemm(EPI_LNFOLD_BF16, a_up, D, fl.wup_f, D, T, H4, D, h->hid, H4, fl.c_up, nullptr, st, &ln)) return 1;
+      } else {
+        if (launch_gemm(EPI_BIAS_BF16, a_up, D, ly.wup, D, T, H4, D, h->hid, H4, ly.bup, nullptr, st)) return 1;
+      }
       if (launch_dwconv_gelu(h->hid, ly.dww9, ly.dwb, h->hid2, batch, h->G, H4, st)) return 1;
     }
-    if (launch_gemm(EPI_BIAS_RESID_F32, h->hid2, H4, ly.wdown, H4, T, D, H4, h->x_res, D, ly.bdown, nullptr, st))
-      return 1;
+    if (fold && l + 1 < h->L) {   // producer of the next block's norm1 inputs (the last block feeds the fp32 out-projection)
+      LnFoldArgs ln{nullptr, nullptr, 0, 1e-5f, h->xb[cur ^ 1], D, h->part[cur ^ 1]};
+      if (launch_gemm(EPI_BIAS_RESID_LNP, h->hid2, H4, ly.wdown, H4, T, D, H4, h->x_res, D, ly.bdown, nullptr, st, &ln)) return 1;
+      cur ^= 1;
+    } else {
+      if (launch_gemm(EPI_BIAS_RESID_F32, h->hid2, H4, ly.wdown, H4, T, D, H4, h->x_res, D, ly.bdown, nullptr, st)) return 1;
+    }
   }
   return launch_outproj(h->x_res, h->out_w, h->out_b, out, batch, h->C, h->img, h->patch, D, st);
 }
 
-static int kernels_per_forward(const tld_denoiser* h) { return 1 + (use_fused_mlp(h) ? 8 : 9) * h->L + 1; }
+static int kernels_per_forward(const tld_denoiser* h) {
+  const int per_layer = 9 - (use_fused_mlp(h) ? 1 : 0) - (use_ln_fold(h) ? 2 : 0);
+  return 1 + (use_ln_fold(h) ? 1 : 0) + per_layer * h->L + 1;
+}
 
 }  // namespace tld
 
@@ -318,6 +389,10 @@ int tld_set_option(const char* key, int value) {
   }
   if (k == "fused_mlp") {
     g_fused_mlp = value != 0;
+    return 0;
+  }
+  if (k == "ln_fold") {
+    g_ln_fold = value != 0;
     return 0;
   }
   if (k == "attention_exp_emu") {
@@ -405,6 +480,7 @@ int tld_denoiser_set_param(tld_denoiser* h, const char* key, const float* data, 
     TLD_CUDA_OK(cudaMemcpy(s.dst, data, (size_t)numel * sizeof(float), cudaMemcpyDefault));
   } else {
     TLD_CUDA_OK(cudaMemcpy(h->staging, data, (size_t)numel * sizeof(float), cudaMemcpyDefault));
+    if (s.shadow) TLD_CUDA_OK(cudaMemcpy(s.shadow, h->staging, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice));
     if (s.kind == P_BF16)
       f32_to_bf16_kernel<<<blocks, thr>>>(h->staging, reinterpret_cast<bf16*>(s.dst), s.numel);
     else
@@ -413,6 +489,7 @@ int tld_denoiser_set_param(tld_denoiser* h, const char* key, const float* data, 
     TLD_CUDA_OK(cudaDeviceSynchronize());
   }
   s.filled = true;
+  h->fold_dirty = true;
   return 0;
 }
 
@@ -453,7 +530,15 @@ int tld_denoiser_set_params_async(tld_denoiser* h, int n, const char* const* key
     e.pad = 0;
     s.filled = true;
     if (filled == REFRESH_BATCH && flush()) return 1;
+    if (s.shadow) {   // the fp32 copy the LayerNorm-folded weights are rebuilt from
+      RefreshEntry& e2 = batch.e[filled++];
+      e2 = e;
+      e2.dst = s.shadow;
+      e2.kind = 0;
+      if (filled == REFRESH_BATCH && flush()) return 1;
+    }
   }
+  h->fold_dirty = true;
   return flush();
 }
 
@@ -485,6 +570,7 @@ int tld_denoiser_forward(tld_denoiser* h, const float* x, const float* noise_lev
                   nullptr, st))
     return 1;
   if (launch_embed(x, batch, batch, h->C, h->img, h->patch, h->D, h->emb, h->x_res, st)) return 1;
+  if (use_ln_fold(h) && ensure_fold(h, st)) return 1;
   return run_blocks(h, batch, h->kv, kvs, h->kv + (size_t)batch * kvs, kvs, nullptr, out, st);
 }
 
@@ -590,6 +676,7 @@ int tld_sampler_generate(tld_denoiser* h, const float* labels, const float* seed
   // rows come FIRST so that every address the captured graph bakes in depends on the batch size alone: a second call
   // with the same batch and a different number of steps replays the same graph on correctly placed rows.
   const long long kvs = (long long)h->L * 2 * h->D;
+  if (use_ln_fold(h) && ensure_fold(h, st)) return 1;
   if (launch_cond_label(labels, Beff, num_imgs, h->Te, h->D, h->cond, h->ycond, h->cond_scratch, st)) return 1;
   if (launch_cond_noise(h->tlevels, calls, h->E, h->D, h->cond, h->ycond + (size_t)Beff * h->D, h->cond_scratch, st))
     return 1;
@@ -671,6 +758,41 @@ int tld_op_gemm_xattn(const uint16_t* A, const uint16_t* Wq, int M, int D, float
                      D, D, x, D, nullptr, &xa, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int tld_op_gemm_lnfold(const uint16_t* A, const uint16_t* Wf, int M, int N, int K, uint16_t* out, const float* col_c,
+                       const float* col_s, const float* row_part, int n_part, void* stream) {
+  LnFoldArgs ln{col_s, reinterpret_cast<const float2*>(row_part), n_part, 1e-5f, nullptr, 0, nullptr};
+  return launch_gemm(EPI_LNFOLD_BF16, reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(Wf), K, M, N, K, out, N,
+                     col_c, nullptr, reinterpret_cast<cudaStream_t>(stream), &ln);
+}
+
+int tld_op_gemm_bias_resid_lnp(const uint16_t* A, const uint16_t* W, int M, int N, int K, float* x, const float* bias,
+                               uint16_t* xb_out, float* part_out, void* stream) {
+  LnFoldArgs ln{nullptr, nullptr, 0, 1e-5f, reinterpret_cast<bf16*>(xb_out), N, reinterpret_cast<float2*>(part_out)};
+  return launch_gemm(EPI_BIAS_RESID_LNP, reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(W), K, M, N, K, x, N,
+                     bias, nullptr, reinterpret_cast<cudaStream_t>(stream), &ln);
+}
+
+int tld_op_gemm_xattn_lnp(const uint16_t* A, const uint16_t* Wq, int M, int D, float* x, const float* kv0, const float* kv1,
+                          int n_tok, uint16_t* xb_out, float* part_out, void* stream) {
+  XattnArgs xa;
+  xa.kv0 = kv0; xa.kv1 = kv1;
+  xa.kv0_stride = 2LL * D; xa.kv1_stride = 2LL * D;
+  xa.step_ptr = nullptr; xa.n_tok = n_tok; xa.embed_dim = D;
+  LnFoldArgs ln{nullptr, nullptr, 0, 1e-5f, reinterpret_cast<bf16*>(xb_out), D, reinterpret_cast<float2*>(part_out)};
+  return launch_gemm(EPI_XATTN_RESID_LNP, reinterpret_cast<const bf16*>(A), D, reinterpret_cast<const bf16*>(Wq), D, M, D, D, x, D,
+                     nullptr, &xa, reinterpret_cast<cudaStream_t>(stream), &ln);
+}
+
+int tld_op_rowstats_cast(const float* x, uint16_t* xb, float* part, int rows, int D, void* stream) {
+  return launch_rowstats_cast(x, reinterpret_cast<bf16*>(xb), reinterpret_cast<float2*>(part), rows, D,
+                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+int tld_op_ln_fold_weights(const float* W, const float* gamma, const float* beta, const float* bias, uint16_t* Wf, float* s,
+                           float* c, int N, int K, void* stream) {
+  return launch_ln_fold_weights(W, gamma, beta, bias, reinterpret_cast<bf16*>(Wf), s, c, N, K, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int tld_op_layernorm(const float* x, const float* gamma, const float* beta, uint16_t* y, int rows, int D,
                      void* stream) {
   return launch_layernorm_bf16(x, gamma, beta, reinterpret_cast<bf16*>(y), rows, D,
@@ -688,8 +810,8 @@ int tld_op_gemm_up_dwconv_gelu(const uint16_t* A, const uint16_t* W, const float
                                const float* row_sums, const float* dw_w9, const float* dw_b, uint16_t* out, int batch, int K,
                                int N, void* stream) {
   return launch_gemm_up_dwconv_gelu(reinterpret_cast<const bf16*>(A), K, reinterpret_cast<const bf16*>(W), K, batch * 256, N, K,
-                                    col_c, col_s, row_sums, 1e-5f, dw_w9, dw_b, reinterpret_cast<bf16*>(out),
-                                    reinterpret_cast<cudaStream_t>(stream));
+                                    col_c, col_s, reinterpret_cast<const float2*>(row_sums), 1, 1e-5f, dw_w9, dw_b,
+                                    reinterpret_cast<bf16*>(out), reinterpret_cast<cudaStream_t>(stream));
 }
 
 int tld_op_dwconv_gelu(const uint16_t* hsrc, const float* w9, const float* bias, uint16_t* g, int batch, int grid,

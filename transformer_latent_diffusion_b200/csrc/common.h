@@ -42,9 +42,26 @@ struct XattnArgs {
   int n_tok;
   int embed_dim;
 };
+// LayerNorm folding (gemm_tcgen05.cuh): consumer side = EPI_LNFOLD_BF16 (col_s, row_part, n_part = K / 32, ln_eps; `bias` is
+// c_n); producer side = EPI_BIAS_RESID_LNP / EPI_XATTN_RESID_LNP (xb_out = bf16 copy of the new rows, part_out [M, N/32])
+struct LnFoldArgs {
+  const float* col_s;
+  const float2* row_part;
+  int n_part;
+  float ln_eps;
+  bf16* xb_out;
+  int ldxb;
+  float2* part_out;
+};
 // C[M,N] = A[M,K] * W[N,K]^T with a fused epilogue (see gemm_tcgen05.cuh). lda/ldw in elements.
 int launch_gemm(int epi, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, void* out, int ldo,
-                const float* bias, const XattnArgs* xa, cudaStream_t st);
+                const float* bias, const XattnArgs* xa, cudaStream_t st, const LnFoldArgs* ln = nullptr);
+// fp32 rows -> bf16 copy + per-32-column (sum, sum of squares) partials [rows, D/32] (the producer side of the LayerNorm fold
+// for rows that no GEMM epilogue produced: the patch embedding)
+int launch_rowstats_cast(const float* x, bf16* xb, float2* part, int rows, int D, cudaStream_t st);
+// W'[n,k] = bf16(gamma[k] W[n,k]); s[n] = sum_k W'[n,k]; c[n] = sum_k beta[k] W[n,k] (+ bias[n])
+int launch_ln_fold_weights(const float* W, const float* gamma, const float* beta, const float* bias, bf16* Wf, float* s,
+                           float* c, int N, int K, cudaStream_t st);
 
 // C[M,N] = A^T B with A stored [K,M], B stored [K,N] (weight-gradient shape, K = tokens); epi = EPI_F32 or EPI_BF16
 int launch_gemm_mn(int epi, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, void* out, int ldo,
@@ -127,8 +144,8 @@ int launch_conv3x3(const bf16* x, const bf16* w, const float* bias, bf16* out, i
                    cudaStream_t st);
 // MLPSepConv front half fused (gemm_dwconv.cu): g = GELU(dwconv3x3(A W^T [LayerNorm-folded] + c) + dw_b) for 16x16-token samples
 int launch_gemm_up_dwconv_gelu(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const float* col_c,
-                               const float* col_s, const float* row_sums, float ln_eps, const float* dw_w9, const float* dw_b,
-                               bf16* out, cudaStream_t st);
+                               const float* col_s, const float2* row_part, int n_part, float ln_eps, const float* dw_w9,
+                               const float* dw_b, bf16* out, cudaStream_t st);
 void set_gemm_ctas(int v);  // 0 auto, 1 single-CTA tiles, 2 CTA-pair tiles (experiments / tests)
 
 // 2-D row-major TMA descriptor (bf16 or fp32), box = [box_rows, 128 bytes], 128B swizzle (gemm.cu)

@@ -78,8 +78,8 @@ int make_tmap_tokens3d(CUtensorMap* m, const void* base, int B, int npos, int C,
 }
 
 template <int BN, int EPI, int CTAS>
-static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
-                    const GemmEpi& ep, cudaStream_t st) {
+static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& td, int M, int N,
+                    int K, const GemmEpi& ep, cudaStream_t st) {
   auto kern = gemm_bf16_tn_kernel<BN, EPI, CTAS>;
   constexpr int smem = GemmSmem<BN, EPI, CTAS>::TOTAL;
   static bool attr_set = false;
@@ -104,19 +104,22 @@ static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensor
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  TLD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, M, N, K, ep));
+  TLD_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, td, M, N, K, ep));
   return 0;
 }
 
 template <int BN, int CTAS>
-static int launch_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
-                     const GemmEpi& ep, cudaStream_t st) {
+static int launch_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& td, int M,
+                     int N, int K, const GemmEpi& ep, cudaStream_t st) {
   switch (epi) {
-    case EPI_BF16: return launch_t<BN, EPI_BF16, CTAS>(ta, tb, tc, M, N, K, ep, st);
-    case EPI_BIAS_BF16: return launch_t<BN, EPI_BIAS_BF16, CTAS>(ta, tb, tc, M, N, K, ep, st);
-    case EPI_BIAS_RESID_F32: return launch_t<BN, EPI_BIAS_RESID_F32, CTAS>(ta, tb, tc, M, N, K, ep, st);
-    case EPI_XATTN_RESID_F32: return launch_t<BN, EPI_XATTN_RESID_F32, CTAS>(ta, tb, tc, M, N, K, ep, st);
-    case EPI_F32: return launch_t<BN, EPI_F32, CTAS>(ta, tb, tc, M, N, K, ep, st);
+    case EPI_BF16: return launch_t<BN, EPI_BF16, CTAS>(ta, tb, tc, td, M, N, K, ep, st);
+    case EPI_BIAS_BF16: return launch_t<BN, EPI_BIAS_BF16, CTAS>(ta, tb, tc, td, M, N, K, ep, st);
+    case EPI_BIAS_RESID_F32: return launch_t<BN, EPI_BIAS_RESID_F32, CTAS>(ta, tb, tc, td, M, N, K, ep, st);
+    case EPI_XATTN_RESID_F32: return launch_t<BN, EPI_XATTN_RESID_F32, CTAS>(ta, tb, tc, td, M, N, K, ep, st);
+    case EPI_F32: return launch_t<BN, EPI_F32, CTAS>(ta, tb, tc, td, M, N, K, ep, st);
+    case EPI_LNFOLD_BF16: return launch_t<BN, EPI_LNFOLD_BF16, CTAS>(ta, tb, tc, td, M, N, K, ep, st);
+    case EPI_BIAS_RESID_LNP: return launch_t<BN, EPI_BIAS_RESID_LNP, CTAS>(ta, tb, tc, td, M, N, K, ep, st);
+    case EPI_XATTN_RESID_LNP: return launch_t<BN, EPI_XATTN_RESID_LNP, CTAS>(ta, tb, tc, td, M, N, K, ep, st);
   }
   return fail("launch_gemm: unknown epilogue " + std::to_string(epi));
 }
@@ -144,8 +147,8 @@ static int pick_bn(int M, int N, int ctas) {
   return best;
 }
 
-static int dispatch(int ctas, int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M,
-                    int N, int K, const GemmEpi& ep, cudaStream_t st);
+static int dispatch(int ctas, int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                    const CUtensorMap& td, int M, int N, int K, const GemmEpi& ep, cudaStream_t st);
 
 // 3x3 'same' convolution as an implicit GEMM on the tcgen05 core: x NHWC bf16 [B,H,W,Cin], w bf16 [Cout, 9*Cin]
 // (K order = (ky, kx, cin)), bias fp32 [Cout] -> out NHWC bf16 [B,H,W,Cout].
@@ -171,38 +174,59 @@ int launch_conv3x3(const bf16* x, const bf16* w, const float* bias, bf16* out, i
   ep.conv_cpb = Cin / 64;
   ep.conv_h = H;
   ep.conv_w = W;
-  return dispatch(ctas, bn, bias ? EPI_BIAS_BF16 : EPI_BF16, ta, tb, tc, (int)M, N, K, ep, st);
+  return dispatch(ctas, bn, bias ? EPI_BIAS_BF16 : EPI_BF16, ta, tb, tc, tc, (int)M, N, K, ep, st);
 }
 
 int launch_gemm(int epi, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, void* out, int ldo,
-                const float* bias, const XattnArgs* xa, cudaStream_t st) {
+                const float* bias, const XattnArgs* xa, cudaStream_t st, const LnFoldArgs* ln) {
   TLD_CHECK(M > 0 && N > 0 && K > 0, "launch_gemm: empty problem");
   TLD_CHECK(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "launch_gemm: K/lda/ldw must be multiples of 8 (16-byte TMA rows)");
   TLD_CHECK(N % 32 == 0, "launch_gemm: N must be a multiple of 32");
   TLD_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
             "launch_gemm: operands must be 16-byte aligned");
-  if (epi == EPI_XATTN_RESID_F32) {
+  if (epi == EPI_XATTN_RESID_F32 || epi == EPI_XATTN_RESID_LNP) {
     TLD_CHECK(xa != nullptr, "launch_gemm: cross-attention epilogue needs XattnArgs");
     TLD_CHECK(N % 64 == 0 && xa->n_tok % 64 == 0, "launch_gemm: cross-attention epilogue needs N and n_tok multiples of 64");
     TLD_CHECK(xa->kv0_stride % 4 == 0 && xa->kv1_stride % 4 == 0 && xa->embed_dim % 4 == 0 &&
                   (reinterpret_cast<uintptr_t>(xa->kv0) & 15) == 0 && (reinterpret_cast<uintptr_t>(xa->kv1) & 15) == 0,
               "launch_gemm: cross-attention K/V rows must be 16-byte aligned (float4 staging)");
   }
-  if (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_RESID_F32)
+  if (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_RESID_F32 || epi == EPI_LNFOLD_BF16 || epi == EPI_BIAS_RESID_LNP)
     TLD_CHECK(bias != nullptr, "launch_gemm: bias epilogues need a bias");
-  const bool out_f32 = !(epi == EPI_BF16 || epi == EPI_BIAS_BF16);
+  const bool lnp = epi == EPI_BIAS_RESID_LNP || epi == EPI_XATTN_RESID_LNP;
+  if (epi == EPI_LNFOLD_BF16)
+    TLD_CHECK(ln && ln->col_s && ln->row_part && ln->n_part == K / 32 && K % 64 == 0 && K <= 1024 &&
+                  (reinterpret_cast<uintptr_t>(ln->row_part) & 15) == 0,
+              "launch_gemm: the LayerNorm-fold epilogue needs col_s, 16-byte aligned row partials [M, K/32] and K % 64 == 0");
+  if (lnp)
+    TLD_CHECK(ln && ln->xb_out && ln->part_out && N % 64 == 0 && ldo == N && ln->ldxb % 8 == 0 &&
+                  (reinterpret_cast<uintptr_t>(ln->xb_out) & 15) == 0,
+              "launch_gemm: the producer epilogues need xb_out, part_out, a dense fp32 output (ldo == N) and N % 64 == 0");
+  const bool out_f32 = !(epi == EPI_BF16 || epi == EPI_BIAS_BF16 || epi == EPI_LNFOLD_BF16);
   TLD_CHECK((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo * (out_f32 ? 4 : 2)) % 16 == 0,
             "launch_gemm: output must be 16-byte aligned with a 16-byte multiple row pitch");
   // CTA pairs pay off once there are enough 256-row tiles to fill the 74 SM pairs
   const int ctas = g_gemm_ctas ? g_gemm_ctas : (M >= 4096 ? 2 : 1);
-  const int bn = pick_bn(M, N, ctas);
-  CUtensorMap ta, tb, tc;
+  int bn = pick_bn(M, N, ctas);
+  if (lnp && ctas == 1 && bn > 128) bn = (N % 128 == 0) ? 128 : 64;   // 96 KB of epilogue slabs: keep >= 3 pipeline stages
+  CUtensorMap ta, tb, tc, td;
   if (make_tmap_2d(&ta, A, false, M, K, lda, GEMM_BM)) return 1;
   if (make_tmap_2d(&tb, W, false, N, K, ldw, bn / ctas)) return 1;
   if (make_tmap_2d(&tc, out, out_f32, M, N, ldo, 32)) return 1;
+  td = tc;
+  if (lnp && make_tmap_2d(&td, ln->xb_out, false, M, N, ln->ldxb, 32)) return 1;
   GemmEpi ep{};
   ep.bias = bias;
   ep.scale = 0.125f;  // 1/sqrt(64)
+  if (ln) {
+    ep.col_s = ln->col_s;
+    ep.row_part = ln->row_part;
+    ep.n_part = ln->n_part;
+    ep.inv_d = 1.f / float(K);
+    ep.ln_eps = ln->ln_eps;
+    ep.x_in = reinterpret_cast<const float*>(out);
+    ep.part_out = ln->part_out;
+  }
   if (xa) {
     ep.kv0 = xa->kv0;
     ep.kv1 = xa->kv1;
@@ -212,7 +236,7 @@ int launch_gemm(int epi, const bf16* A, int lda, const bf16* W, int ldw, int M, 
     ep.n_tok = xa->n_tok;
     ep.embed_dim = xa->embed_dim;
   }
-  return dispatch(ctas, bn, epi, ta, tb, tc, M, N, K, ep, st);
+  return dispatch(ctas, bn, epi, ta, tb, tc, td, M, N, K, ep, st);
 }
 
 // MN-major operand modes (see GemmEpi::mn_major).  a_mn: A stored [K, M] instead of [M, K]; b_mn: B stored [K, N] instead of
@@ -245,7 +269,7 @@ static int launch_gemm_major(int epi, bool a_mn, bool b_mn, const bf16* A, int l
   if (make_tmap_2d(&tc, out, out_f32, M, N, ldo, 32)) return 1;
   GemmEpi ep{};
   ep.mn_major = (a_mn ? 1 : 0) | (b_mn ? 2 : 0);
-  return dispatch(ctas, bn, epi, ta, tb, tc, M, N, K, ep, st);
+  return dispatch(ctas, bn, epi, ta, tb, tc, tc, M, N, K, ep, st);
 }
 // C[M,N] = A^T B: the weight-gradient shape dW = dY^T X (K = tokens)
 int launch_gemm_mn(int epi, const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, void* out, int ldo,
@@ -258,21 +282,21 @@ int launch_gemm_nn(int epi, const bf16* A, int lda, const bf16* B, int ldb, int 
   return launch_gemm_major(epi, false, true, A, lda, B, ldb, M, N, K, out, ldo, st);
 }
 
-static int dispatch(int ctas, int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M,
-                    int N, int K, const GemmEpi& ep, cudaStream_t st) {
+static int dispatch(int ctas, int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                    const CUtensorMap& td, int M, int N, int K, const GemmEpi& ep, cudaStream_t st) {
   if (ctas == 2) {
     switch (bn) {
-      case 256: return launch_bn<256, 2>(epi, ta, tb, tc, M, N, K, ep, st);
-      case 192: return launch_bn<192, 2>(epi, ta, tb, tc, M, N, K, ep, st);
-      case 128: return launch_bn<128, 2>(epi, ta, tb, tc, M, N, K, ep, st);
-      case 64: return launch_bn<64, 2>(epi, ta, tb, tc, M, N, K, ep, st);
+      case 256: return launch_bn<256, 2>(epi, ta, tb, tc, td, M, N, K, ep, st);
+      case 192: return launch_bn<192, 2>(epi, ta, tb, tc, td, M, N, K, ep, st);
+      case 128: return launch_bn<128, 2>(epi, ta, tb, tc, td, M, N, K, ep, st);
+      case 64: return launch_bn<64, 2>(epi, ta, tb, tc, td, M, N, K, ep, st);
     }
   }
   switch (bn) {
-    case 256: return launch_bn<256, 1>(epi, ta, tb, tc, M, N, K, ep, st);
-    case 192: return launch_bn<192, 1>(epi, ta, tb, tc, M, N, K, ep, st);
-    case 128: return launch_bn<128, 1>(epi, ta, tb, tc, M, N, K, ep, st);
-    case 64: return launch_bn<64, 1>(epi, ta, tb, tc, M, N, K, ep, st);
+    case 256: return launch_bn<256, 1>(epi, ta, tb, tc, td, M, N, K, ep, st);
+    case 192: return launch_bn<192, 1>(epi, ta, tb, tc, td, M, N, K, ep, st);
+    case 128: return launch_bn<128, 1>(epi, ta, tb, tc, td, M, N, K, ep, st);
+    case 64: return launch_bn<64, 1>(epi, ta, tb, tc, td, M, N, K, ep, st);
   }
   return fail("gemm dispatch: no tile width for N=" + std::to_string(N));
 }

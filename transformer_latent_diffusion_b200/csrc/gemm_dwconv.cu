@@ -42,7 +42,8 @@ namespace tld {
 struct FusedUpArgs {
   const float* col_c;      // [N] c_n (bias, or bias + sum_k beta_k W_nk with the LayerNorm fold)
   const float* col_s;      // [N] s_n = sum_k W'_nk (LayerNorm fold) or nullptr
-  const float2* row_sums;  // [M] (sum, sum of squares) of the fp32 residual row (LayerNorm fold) or nullptr
+  const float2* row_part;  // [M, n_part] partial (sum, sum of squares) of the fp32 residual row (LayerNorm fold) or nullptr
+  int n_part;              // partials per row (K / 32 when a GEMM epilogue produced them)
   float inv_d, ln_eps;     // 1/D and epsilon of the folded LayerNorm
   const float* dw_w9;      // [9, N] depthwise taps, tap-major
   const float* dw_b;       // [N]
@@ -204,11 +205,19 @@ gemm_up_dwconv_gelu_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
         cs[FU_BN + 128 + et] = __ldg(ep.col_s + n0 + 128 + et);
       }
       float ar = 1.f, br = 0.f;          // value = ar * acc + (br * s_n + c_n)
-      if (ep.row_sums) {
-        const float2 ss = __ldg(ep.row_sums + m0 + et);
-        const float mean = ss.x * ep.inv_d;
-        const float var = fmaxf(ss.y * ep.inv_d - mean * mean, 0.f);
-        ar = rsqrtf(var + ep.ln_eps);
+      if (ep.row_part) {
+        const float2* pp = ep.row_part + (size_t)(m0 + et) * ep.n_part;
+        float2 pv[32];   // all partials of the row in flight at once (K <= 1024), then a fixed-order (deterministic) sum
+#pragma unroll
+        for (int u = 0; u < 32; ++u) pv[u] = u < ep.n_part ? __ldg(pp + u) : make_float2(0.f, 0.f);
+        float ps = 0.f, pq = 0.f;
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          ps += pv[u].x;
+          pq += pv[u].y;
+        }
+        const float mean = ps * ep.inv_d;
+        ar = rsqrtf(fmaxf(pq * ep.inv_d - mean * mean, 0.f) + ep.ln_eps);
         br = -ar * mean;
       }
       named_bar_sync(1, 128);
@@ -339,16 +348,17 @@ gemm_up_dwconv_gelu_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
 
 // g[M, N] = GELU(dwconv3x3(A[M,K] W[N,K]^T (LN-folded) + c) + dw_b), M = batch * 256 tokens (16 x 16 grid per sample)
 int launch_gemm_up_dwconv_gelu(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const float* col_c,
-                               const float* col_s, const float* row_sums, float ln_eps, const float* dw_w9, const float* dw_b,
-                               bf16* out, cudaStream_t st) {
+                               const float* col_s, const float2* row_part, int n_part, float ln_eps, const float* dw_w9,
+                               const float* dw_b, bf16* out, cudaStream_t st) {
   TLD_CHECK(M > 0 && M % 256 == 0, "gemm_up_dwconv: rows must be whole 16x16-token samples (M % 256 == 0)");
   TLD_CHECK(N > 0 && N % FU_BN == 0, "gemm_up_dwconv: hidden width must be a multiple of 256");
   TLD_CHECK(K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm_up_dwconv: K/lda/ldw must be multiples of 8");
   TLD_CHECK(col_c && dw_w9 && dw_b && out, "gemm_up_dwconv: null argument");
-  TLD_CHECK((col_s == nullptr) == (row_sums == nullptr), "gemm_up_dwconv: the LayerNorm fold needs both col_s and row_sums");
+  TLD_CHECK((col_s == nullptr) == (row_part == nullptr) && (row_part == nullptr || (n_part > 0 && n_part <= 32)),
+            "gemm_up_dwconv: the LayerNorm fold needs both col_s and the row partials");
   TLD_CHECK(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(out) |
               reinterpret_cast<uintptr_t>(col_c) | reinterpret_cast<uintptr_t>(col_s) | reinterpret_cast<uintptr_t>(dw_w9) |
-              reinterpret_cast<uintptr_t>(dw_b) | reinterpret_cast<uintptr_t>(row_sums)) & 15) == 0,
+              reinterpret_cast<uintptr_t>(dw_b)) & 15) == 0 && (reinterpret_cast<uintptr_t>(row_part) & 7) == 0,
             "gemm_up_dwconv: operands must be 16-byte aligned");
   CUtensorMap ta, tb;
   if (make_tmap_2d(&ta, A, false, M, K, lda, 128)) return 1;
@@ -356,7 +366,8 @@ int launch_gemm_up_dwconv_gelu(const bf16* A, int lda, const bf16* W, int ldw, i
   FusedUpArgs ep{};
   ep.col_c = col_c;
   ep.col_s = col_s;
-  ep.row_sums = reinterpret_cast<const float2*>(row_sums);
+  ep.row_part = row_part;
+  ep.n_part = n_part;
   ep.inv_d = 1.f / float(K);
   ep.ln_eps = ln_eps;
   ep.dw_w9 = dw_w9;

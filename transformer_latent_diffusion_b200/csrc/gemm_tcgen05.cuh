@@ -27,6 +27,12 @@
 //   EPI_BIAS_RESID_F32  x_f32   += acc + bias                            mlp.3 1x1 conv + "+x" (:104,:138)
 //   EPI_XATTN_RESID_F32 x_f32   += softmax2(q.k0, q.k1) . (v0, v1)       q_linear + 2-key SDPA + "+x" (:70-72,:137)
 //   EPI_F32             out_f32  = acc                                   kv_linear on cond tokens (:71)
+// LayerNorm folding (the norm1 / norm3 kernels disappear; their statistics ride on the residual epilogues):
+//   EPI_LNFOLD_BF16     out_bf16 = rstd_r (acc - mean_r s_n) + c_n               consumer: A = bf16(x) un-normalised, W = gamma (.) W,
+//                        s_n = sum_k W'_nk, c_n = sum_k beta_k W_nk (+ bias); mean / rstd from per-32-column (sum, sum of
+//                        squares) partials of the fp32 row written by the producer of x
+//   EPI_BIAS_RESID_LNP  x_f32 = x_f32 + acc + bias (explicit read-modify-write), plus the bf16 copy of the new row (tmap_d) and its
+//   EPI_XATTN_RESID_LNP per-32-column (sum, sum of squares) partials: the producer side, for mlp.3 and for the cross-attention
 #pragma once
 #include "ptx.cuh"
 
@@ -38,6 +44,9 @@ enum EpiMode : int {
   EPI_BIAS_RESID_F32 = 2,
   EPI_XATTN_RESID_F32 = 3,
   EPI_F32 = 4,
+  EPI_LNFOLD_BF16 = 5,
+  EPI_BIAS_RESID_LNP = 6,
+  EPI_XATTN_RESID_LNP = 7,
 };
 
 struct GemmEpi {
@@ -59,6 +68,14 @@ struct GemmEpi {
   // [64 k x 64 mn] TMA boxes and fed to tcgen05.mma as an MN-major tile (idesc a/b_major = 1), so no transposed copies of
   // activations or weights are ever written.
   int mn_major;
+  // LayerNorm fold, consumer side (EPI_LNFOLD_BF16): bias = c_n, col_s = s_n, row_part [M, n_part] partial row statistics
+  const float* col_s;
+  const float2* row_part;
+  int n_part;               // K / 32 partials per row
+  float inv_d, ln_eps;      // 1 / K and the LayerNorm epsilon
+  // producer side (EPI_*_LNP): x_in == the fp32 output (read thread = row before it is overwritten), part_out [M, N / 32]
+  const float* x_in;
+  float2* part_out;
 };
 
 constexpr int GEMM_BM = 128;
@@ -72,12 +89,23 @@ struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = (BN / CTAS) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STG_BYTES = 4 * 2 * STG_SLAB;  // 4 warps x 2 buffers
-  static constexpr int KV_BYTES = (EPI == EPI_XATTN_RESID_F32) ? 2 * 2 * 4 * BN * 4 : 0;  // 2 buffers x 2 samples x {k0,k1,v0,v1}
-  static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - STG_BYTES - KV_BYTES - 256 /*barriers*/;
+  static constexpr bool LNP = (EPI == EPI_BIAS_RESID_LNP || EPI == EPI_XATTN_RESID_LNP);
+  // plain modes: 4 warps x 2 staging slabs.  Producer modes: 4 warps x (LNP_SLABS in-place fp32 slabs: TMA load of x_old ->
+  // read-modify-write in shared memory -> TMA store of x_new, 2 chunks of prefetch) + 2 slabs for the bf16 copy
+  // mlp.3 (K = 4D, long main loop, epilogue has slack): 2 in-place slabs + 1 bf16 slab keep 6 pipeline stages for the
+  // DRAM-streamed A operand; cross-attention (K = D, epilogue-bound): 4 in-place slabs (2 chunks of prefetch) + 2 bf16 slabs
+  static constexpr int LNP_SLABS = EPI == EPI_XATTN_RESID_LNP ? 4 : 2;
+  static constexpr int LNP_BF16_SLABS = EPI == EPI_XATTN_RESID_LNP ? 2 : 1;
+  static constexpr int STG_BYTES = LNP ? 4 * (LNP_SLABS + LNP_BF16_SLABS) * STG_SLAB : 4 * 2 * STG_SLAB;
+  // cross-attention: 2 buffers x 2 samples x {k0,k1,v0,v1};  LayerNorm-fold consumer: 2 buffers x {c_n, s_n} of the tile's columns
+  static constexpr int KV_BYTES = (EPI == EPI_XATTN_RESID_F32 || EPI == EPI_XATTN_RESID_LNP) ? 2 * 2 * 4 * BN * 4
+                                  : (EPI == EPI_LNFOLD_BF16 ? 2 * 2 * BN * 4 : 0);
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - STG_BYTES - KV_BYTES - 512 /*barriers*/;
   static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
-  static constexpr int TOTAL = 1024 + STAGES * STAGE_BYTES + STG_BYTES + KV_BYTES + 256;
-  static_assert(STAGES >= 3, "not enough shared memory for a 3-stage pipeline");
+  static constexpr int TOTAL = 1024 + STAGES * STAGE_BYTES + STG_BYTES + KV_BYTES + 512;
+  // producer modes keep 96 KB of slabs: their wide single-CTA tiles would be left with 2 stages and are never dispatched
+  // (launch_gemm narrows BN to <= 128 for them)
+  static_assert(STAGES >= (LNP ? 2 : 3), "not enough shared memory for the pipeline");
 };
 
 // write this lane's 128-byte row into a 128B-swizzled [32 x 128 B] slab (conflict-free per quarter-warp)
@@ -90,7 +118,8 @@ __device__ __forceinline__ void stage_row(uint8_t* slab, int lane, const uint32_
 template <int BN, int EPI, int CTAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K, GemmEpi ep) {
+                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_d, int M, int N, int K,
+                    GemmEpi ep) {
   using S = GemmSmem<BN, EPI, CTAS>;
   static_assert(CTAS == 1 || CTAS == 2, "CTAS must be 1 or 2");
   const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
@@ -98,8 +127,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   constexpr int STAGES = S::STAGES;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                  : (2 * BN <= 256) ? 256 : 512;
-  constexpr bool OUT_BF16 = (EPI == EPI_BF16 || EPI == EPI_BIAS_BF16);
+  constexpr bool OUT_BF16 = (EPI == EPI_BF16 || EPI == EPI_BIAS_BF16 || EPI == EPI_LNFOLD_BF16);
   constexpr bool REDUCE = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_XATTN_RESID_F32);
+  constexpr bool XATTN = (EPI == EPI_XATTN_RESID_F32 || EPI == EPI_XATTN_RESID_LNP);
+  constexpr bool LNP = (EPI == EPI_BIAS_RESID_LNP || EPI == EPI_XATTN_RESID_LNP);
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN must be 64..256, multiple of 64");
 
   extern __shared__ uint8_t smem_raw[];
@@ -114,6 +145,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* lnp_bar = bars + 2 * STAGES + 5;    // [4 warps][LNP_SLABS]: x_old slab loaded (producer modes)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -130,6 +162,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_c);
+    if constexpr (LNP) tma_prefetch_desc(&tmap_d);
   }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < STAGES; ++s) {
@@ -140,6 +173,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 4 * CTAS);  // one arrive per epilogue warp of every CTA in the pair
     }
+    if constexpr (LNP)
+      for (int s = 0; s < 4 * S::LNP_SLABS; ++s) mbar_init(&lnp_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -165,6 +200,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * GEMM_BM;
         const int n0 = (tile % n_tiles) * BN + int(cta_rank) * (BN / CTAS);
+        if constexpr (LNP) {
+          // producer modes: pull the fp32 residual tile the epilogue will read-modify-write one tile from now into L2, so
+          // that its slab loads see L2 latency instead of DRAM latency
+          const int tn = tile + tile_step;
+          if (tn < num_tiles) {
+            const int pm = (tn / n_tiles) * TILE_M + int(cta_rank) * GEMM_BM, pn = (tn % n_tiles) * BN;
+            for (int r = 0; r < GEMM_BM; r += 32)
+              for (int c = 0; c < BN; c += 32)
+                if (pm + r < M && pn + c < N) tma_prefetch_2d(&tmap_c, pn + c, pm + r);
+          }
+        }
         // implicit-GEMM conv: first pixel of this CTA's 128-row tile -> (image, y, x)
         int cimg = 0, cy0 = 0, cx0 = 0;
         if (ep.conv_cpb > 0) {
@@ -307,11 +353,76 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       buf ^= 1;
     };
+    // ---- producer modes: the fp32 residual goes through shared memory in place.  Per warp LNP_SLABS slabs [32 rows x 32
+    // columns fp32, 128B-swizzled]: chunk q of this warp's chunk sequence (tiles in order, BN/32 chunks each) uses slab q % 4;
+    // x_old arrives by TMA (issued two chunks ahead), every lane adds its row's new values in place, the same slab leaves by
+    // TMA store.  One bulk group per chunk and one per 64-column bf16 copy (committed even when nothing is stored), so that
+    // "all but the 2 latest groups have been read" == the slab of chunk q - 2 is free to be refilled with chunk q + 2.
+    constexpr int NCH = BN / 32;
+    uint8_t* pslab = smem_stg + ew * (S::LNP_SLABS + S::LNP_BF16_SLABS) * STG_SLAB;
+    uint64_t* my_ld_bar = lnp_bar + ew * S::LNP_SLABS;
+    int q_chunk = 0;   // chunks this warp has processed so far
+    int q_pair = 0;    // 64-column bf16 copies this warp has stored so far (their two slabs alternate strictly)
+    auto lnp_issue = [&](int tile_, int ch_, int q_) {   // lane 0: fetch x_old of chunk (tile_, ch_) into slab q_ % LNP_SLABS
+      const int srow = (tile_ / n_tiles) * TILE_M + int(cta_rank) * GEMM_BM + ew * 32;
+      const int col = (tile_ % n_tiles) * BN + ch_ * 32;
+      if (srow < M && col < N) {
+        const int sl = q_ % S::LNP_SLABS;
+        mbar_expect_tx(&my_ld_bar[sl], STG_SLAB);
+        tma_load_2d(pslab + sl * STG_SLAB, &tmap_c, &my_ld_bar[sl], col, srow);
+      }
+    };
+    // x_old of this lane's row, chunk q_chunk (zeros if the slab is out of range); the caller overwrites it with x_new
+    auto lnp_wait = [&](int srow, int col) -> uint32_t {
+      const int sl = q_chunk % S::LNP_SLABS;
+      if (srow < M && col < N) mbar_wait(&my_ld_bar[sl], uint32_t(q_chunk / S::LNP_SLABS) & 1u);
+      return smem_u32(pslab + sl * STG_SLAB) + lane * 128;
+    };
+    // start of a chunk: with 4 slabs recycle the slab of chunk q - 2 for chunk q + 2 (at most 2 younger groups exist: no
+    // stall); with 2 slabs the other slab (chunk q - 1, every group read) is refilled with chunk q + 1
+    auto lnp_advance = [&](int tile_, int ch_) {
+      constexpr int AHEAD = S::LNP_SLABS == 4 ? 2 : 1;
+      if (lane == 0) {
+        if constexpr (S::LNP_SLABS == 4) bulk_wait_read<2>();
+        else bulk_wait_read<0>();
+        int ch2 = ch_ + AHEAD, tile2 = tile_;
+        if (ch2 >= NCH) { ch2 -= NCH; tile2 += tile_step; }
+        if (tile2 < num_tiles) lnp_issue(tile2, ch2, q_chunk + AHEAD);
+      }
+      __syncwarp();
+    };
+    auto lnp_store = [&](uint32_t slab_lane_addr, int srow, int col) {   // after the lanes rewrote their rows in place
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (srow < M && col < N) tma_store_2d(&tmap_c, pslab + (q_chunk % S::LNP_SLABS) * STG_SLAB, col, srow);
+        bulk_commit();
+      }
+      ++q_chunk;
+    };
+    auto lnp_store_bf16 = [&](const uint32_t (&ob)[32], int srow, int col) {
+      // previous use of this slab: 6 groups back with two slabs, 3 groups back (and every group read) with one
+      uint8_t* slab = pslab + (S::LNP_SLABS + (q_pair % S::LNP_BF16_SLABS)) * STG_SLAB;
+      ++q_pair;
+      stage_row(slab, lane, ob);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (srow < M && col < N) tma_store_2d(&tmap_d, slab, col, srow);
+        bulk_commit();
+      }
+    };
+    if constexpr (LNP) {
+      if (lane == 0 && first_tile < num_tiles) {
+        lnp_issue(first_tile, 0, 0);
+        if constexpr (S::LNP_SLABS == 4) lnp_issue(first_tile, 1, 1);
+      }
+    }
 
     // cross-attention K/V staging (EPI_XATTN_RESID_F32 only): 2 samples x 4 vectors x BN columns as float4 pieces
     constexpr int KV_LD = (2 * BN + 127) / 128;   // float4 loads per thread
     float4 kv_pre[KV_LD];
-    const long long r0s = (EPI == EPI_XATTN_RESID_F32 && ep.step_ptr) ? (long long)(*ep.step_ptr) : -1;
+    const long long r0s = (XATTN && ep.step_ptr) ? (long long)(*ep.step_ptr) : -1;
     auto kv_fetch = [&](int tile) {
       const int m0 = (tile / n_tiles) * TILE_M + int(cta_rank) * GEMM_BM;
       const int n0 = (tile % n_tiles) * BN;
@@ -340,7 +451,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                  __float_as_uint(kv_pre[u].w));
       }
     };
-    if constexpr (EPI == EPI_XATTN_RESID_F32) {
+    if constexpr (XATTN) {
       if (first_tile < num_tiles) kv_fetch(first_tile);
     }
 
@@ -355,7 +466,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
       int sidx = 0;
       uint32_t kvb = 0;
-      if constexpr (EPI == EPI_XATTN_RESID_F32) {
+      if constexpr (XATTN) {
         // k0,k1,v0,v1 of the (at most two) samples this tile touches: fetched into registers one tile ahead (the global
         // loads are in flight during the previous tile's epilogue math), parked in smem buffer it & 1.  One barrier per
         // tile suffices: whoever writes buffer it & 1 has passed barrier it-1, which every reader of tile it-2 reached
@@ -368,11 +479,44 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         kvb += sidx * 4 * BN * 4;
       }
 
+      float ln_a = 1.f, ln_b = 0.f;   // EPI_LNFOLD_BF16: value = ln_a * acc + (ln_b * s_n + c_n)
+      uint32_t cs_u32 = 0;
+      if constexpr (EPI == EPI_LNFOLD_BF16) {
+        // the tile's column constants through shared memory (every thread needs every column: broadcast LDS.128 instead of
+        // two uniform global loads per column pair).  Buffer it & 1; the barrier of tile it + 1 fences its readers.
+        float* cs = smem_kv + (it & 1) * (2 * BN);
+#pragma unroll
+        for (int u = 0; u < (BN + 127) / 128; ++u) {
+          const int c = et + 128 * u;
+          if (c < BN) {
+            const bool ok = n0 + c < N;
+            cs[c] = ok ? __ldg(ep.bias + n0 + c) : 0.f;
+            cs[BN + c] = ok ? __ldg(ep.col_s + n0 + c) : 0.f;
+          }
+        }
+        named_bar_sync(1, 128);
+        cs_u32 = smem_u32(cs);
+        if (row < M) {
+          const float4* pp = reinterpret_cast<const float4*>(ep.row_part + (size_t)row * ep.n_part);
+          float4 pv[16];   // all partials of the row in flight at once (K <= 1024): a dependent load chain per tile costs more
+#pragma unroll       // than the tile's MMAs
+          for (int u = 0; u < 16; ++u) pv[u] = u < ep.n_part / 2 ? __ldg(pp + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float ps = 0.f, pq = 0.f;
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {   // fixed order: deterministic
+            ps += pv[u].x + pv[u].z;
+            pq += pv[u].y + pv[u].w;
+          }
+          const float mean = ps * ep.inv_d;
+          ln_a = rsqrtf(fmaxf(pq * ep.inv_d - mean * mean, 0.f) + ep.ln_eps);
+          ln_b = -ln_a * mean;
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + acc * BN;
 
-      if constexpr (EPI == EPI_XATTN_RESID_F32) {
+      if constexpr (XATTN) {
 #pragma unroll 1
         for (int hc = 0; hc < BN / 64; ++hc) {
           uint32_t qa[32], qb[32];
@@ -399,21 +543,49 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx);
           const float inv = 1.f / (e0 + e1);
           const float p0 = e0 * inv, p1 = e1 * inv;
+          uint32_t ob[LNP ? 32 : 1];   // producer mode: the 64 columns of this head as bf16 pairs
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
+            const int col = n0 + hc * 64 + half * 32;
+            uint32_t xin = 0;
+            if constexpr (LNP) {
+              lnp_advance(tile, hc * 2 + half);
+              xin = lnp_wait(slab_row, col);
+            }
+            const bool have_x = LNP && slab_row < M && col < N;
             uint32_t o[32];
+            float ps = 0.f, pq = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 a = lds_v4(v0 + (half * 8 + i) * 16), b = lds_v4(v1 + (half * 8 + i) * 16);
-              o[4 * i] = __float_as_uint(p0 * a.x + p1 * b.x);
-              o[4 * i + 1] = __float_as_uint(p0 * a.y + p1 * b.y);
-              o[4 * i + 2] = __float_as_uint(p0 * a.z + p1 * b.z);
-              o[4 * i + 3] = __float_as_uint(p0 * a.w + p1 * b.w);
+              float w0 = p0 * a.x + p1 * b.x, w1 = p0 * a.y + p1 * b.y, w2 = p0 * a.z + p1 * b.z, w3 = p0 * a.w + p1 * b.w;
+              if constexpr (LNP) {
+                if (have_x) {
+                  const float4 xo = lds_v4(xin + ((i ^ (lane & 7)) << 4));
+                  w0 += xo.x; w1 += xo.y; w2 += xo.z; w3 += xo.w;
+                }
+                ps += (w0 + w1) + (w2 + w3);
+                pq += (w0 * w0 + w1 * w1) + (w2 * w2 + w3 * w3);
+                ob[half * 16 + 2 * i] = pack_bf16x2(w0, w1);
+                ob[half * 16 + 2 * i + 1] = pack_bf16x2(w2, w3);
+              }
+              o[4 * i] = __float_as_uint(w0);
+              o[4 * i + 1] = __float_as_uint(w1);
+              o[4 * i + 2] = __float_as_uint(w2);
+              o[4 * i + 3] = __float_as_uint(w3);
             }
-            uint8_t* slab = slab_acquire();
-            stage_row(slab, lane, o);
-            slab_release(slab, n0 + hc * 64 + half * 32, slab_row);
+            if constexpr (LNP) {
+              if (row < M && col < N) ep.part_out[(size_t)row * (N / 32) + col / 32] = make_float2(ps, pq);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) sts_v4(xin + ((j ^ (lane & 7)) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+              lnp_store(xin, slab_row, col);
+            } else {
+              uint8_t* slab = slab_acquire();
+              stage_row(slab, lane, o);
+              slab_release(slab, col, slab_row);
+            }
           }
+          if constexpr (LNP) lnp_store_bf16(ob, slab_row, n0 + hc * 64);
         }
       } else if constexpr (OUT_BF16) {
 #pragma unroll 1
@@ -439,12 +611,63 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 g0 += b1.x; g1 += b1.y;
               }
             }
+            if constexpr (EPI == EPI_LNFOLD_BF16) {   // out-of-range columns hold zeros and are clipped by the TMA store
+              const uint32_t cb = cs_u32 + (ch * 64 + 2 * i) * 4;
+              float c0x, c0y, s0x, s0y, c1x, c1y, s1x, s1y;
+              asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(c0x), "=f"(c0y) : "r"(cb));
+              asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(s0x), "=f"(s0y) : "r"(cb + BN * 4));
+              asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(c1x), "=f"(c1y) : "r"(cb + 128));
+              asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(s1x), "=f"(s1y) : "r"(cb + BN * 4 + 128));
+              f0 = fmaf(ln_a, f0, fmaf(ln_b, s0x, c0x));
+              f1 = fmaf(ln_a, f1, fmaf(ln_b, s0y, c0y));
+              g0 = fmaf(ln_a, g0, fmaf(ln_b, s1x, c1x));
+              g1 = fmaf(ln_a, g1, fmaf(ln_b, s1y, c1y));
+            }
             o[i] = pack_bf16x2(f0, f1);
             o[16 + i] = pack_bf16x2(g0, g1);
           }
           uint8_t* slab = slab_acquire();
           stage_row(slab, lane, o);
           slab_release(slab, col, slab_row);
+        }
+      } else if constexpr (EPI == EPI_BIAS_RESID_LNP) {
+        // x_new = x_old + acc + bias written back explicitly (fp32), plus its bf16 copy and the row-statistics partials
+#pragma unroll 1
+        for (int cp = 0; cp < BN / 64; ++cp) {
+          uint32_t ob[32];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int ch = cp * 2 + hh;
+            const int col = n0 + ch * 32;
+            lnp_advance(tile, ch);
+            uint32_t r[32];
+            tmem_ld_x32(taddr + ch * 32, r);
+            tmem_ld_wait();
+            const uint32_t xin = lnp_wait(slab_row, col);
+            float ps = 0.f, pq = 0.f;
+            const bool live = col + 31 < N;
+            const bool have_x = slab_row < M && col < N;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = live ? __ldg(reinterpret_cast<const float4*>(ep.bias + col) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4 xo = have_x ? lds_v4(xin + ((i ^ (lane & 7)) << 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float w0 = __uint_as_float(r[4 * i]) + b.x + xo.x, w1 = __uint_as_float(r[4 * i + 1]) + b.y + xo.y;
+              const float w2 = __uint_as_float(r[4 * i + 2]) + b.z + xo.z, w3 = __uint_as_float(r[4 * i + 3]) + b.w + xo.w;
+              ps += (w0 + w1) + (w2 + w3);
+              pq += (w0 * w0 + w1 * w1) + (w2 * w2 + w3 * w3);
+              ob[hh * 16 + 2 * i] = pack_bf16x2(w0, w1);
+              ob[hh * 16 + 2 * i + 1] = pack_bf16x2(w2, w3);
+              r[4 * i] = __float_as_uint(w0);
+              r[4 * i + 1] = __float_as_uint(w1);
+              r[4 * i + 2] = __float_as_uint(w2);
+              r[4 * i + 3] = __float_as_uint(w3);
+            }
+            if (row < M && live) ep.part_out[(size_t)row * (N / 32) + col / 32] = make_float2(ps, pq);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sts_v4(xin + ((j ^ (lane & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            lnp_store(xin, slab_row, col);
+          }
+          lnp_store_bf16(ob, slab_row, n0 + cp * 64);
         }
       } else {
 #pragma unroll 1

@@ -13,6 +13,7 @@ enum PackKind { P_F32, P_BF16, P_TRANSPOSE_F32 };
 struct Slot {
   PackKind kind;
   void* dst;
+  float* shadow = nullptr;  // optional fp32 copy (weights that are also folded with a LayerNorm's gamma)
   long long numel;
   int rows, cols;  // for P_TRANSPOSE_F32: source is [rows, cols]
   bool filled;
@@ -41,6 +42,15 @@ struct tld_denoiser {
   };
   std::vector<Layer> layers;
   bf16* wkv_all = nullptr;  // [L*2D, D]
+  // LayerNorm fold (inference path, gemm_tcgen05.cuh): norm1 -> qkv_linear and norm3 -> mlp.0.  W' = bf16(gamma (.) W) with the
+  // column constants s_n = sum_k W'_nk, c_n = sum_k beta_k W_nk (+ bias), rebuilt from fp32 shadows whenever a parameter changed
+  struct LayerFold {
+    float *wqkv32, *wup32;          // fp32 shadows of the two foldable weights
+    bf16 *wqkv_f, *wup_f;
+    float *s_qkv, *c_qkv, *s_up, *c_up;
+  };
+  std::vector<LayerFold> fold;
+  bool fold_dirty = true;
 
   // activation workspace, sized for ws_batch samples
   int ws_batch = 0;
@@ -50,6 +60,8 @@ struct tld_denoiser {
   bf16* hid = nullptr;      // [T, 4D]
   bf16* hid2 = nullptr;     // [T, 4D]
   float* model_out = nullptr;  // [B, C, H, W]
+  bf16* xb[2] = {nullptr, nullptr};       // bf16 copy of the residual stream, ping-pong (producer epilogues write the other one)
+  float2* part[2] = {nullptr, nullptr};   // [T, D/32] per-32-column (sum, sum of squares) partials of the residual rows
   // conditioning workspace
   int ws_cond_rows = 0;
   bf16* ycond = nullptr;    // [rows, D]

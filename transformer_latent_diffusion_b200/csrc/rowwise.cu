@@ -82,6 +82,86 @@ int launch_layernorm_bf16(const float* x, const float* gamma, const float* beta,
 }
 
 // --------------------------------------------------------------------------------------------
+// LayerNorm fold, producer side for rows no GEMM epilogue wrote (the patch embedding): fp32 row -> bf16 copy + per-32-column
+// (sum, sum of squares) partials [rows, D/32].  One warp per row; lane l holds columns 128 j + 4 l .. + 3, so a 32-column
+// group is 8 consecutive lanes (xor-shuffle 1, 2, 4).  HBM-bound (D * 6 bytes per row), once per forward.
+// --------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(256) rowstats_cast_kernel(const float* __restrict__ x, bf16* __restrict__ xb,
+                                                            float2* __restrict__ part, int rows) {
+  constexpr int D = V * 128;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+  uint2* yr = reinterpret_cast<uint2*>(xb + (size_t)row * D);
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const float4 v = xr[lane + 32 * j];
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    yr[lane + 32 * j] = o;
+    float ps = (v.x + v.y) + (v.z + v.w), pq = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+#pragma unroll
+    for (int o2 = 1; o2 < 8; o2 <<= 1) {
+      ps += __shfl_xor_sync(0xffffffffu, ps, o2);
+      pq += __shfl_xor_sync(0xffffffffu, pq, o2);
+    }
+    if ((lane & 7) == 0) part[(size_t)row * (D / 32) + 4 * j + (lane >> 3)] = make_float2(ps, pq);
+  }
+}
+
+int launch_rowstats_cast(const float* x, bf16* xb, float2* part, int rows, int D, cudaStream_t st) {
+  TLD_CHECK(D % 128 == 0 && D >= 128 && D <= 1024, "rowstats_cast: embed_dim must be a multiple of 128 in [128,1024]");
+  const int grid = (rows + 7) / 8;
+  switch (D / 128) {
+#define RS_CASE(V) \
+  case V: rowstats_cast_kernel<V><<<grid, 256, 0, st>>>(x, xb, part, rows); break;
+    RS_CASE(1) RS_CASE(2) RS_CASE(3) RS_CASE(4) RS_CASE(5) RS_CASE(6) RS_CASE(7) RS_CASE(8)
+#undef RS_CASE
+  }
+  TLD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// LayerNorm fold, weight side: W'[n,k] = bf16(gamma[k] W[n,k]), s[n] = sum_k float(W'[n,k]) (the ROUNDED weights: the
+// epilogue subtracts mean * s from an accumulator that was built from them), c[n] = sum_k beta[k] W[n,k] + bias[n].
+// One warp per output row; runs once per weight refresh.
+__global__ void __launch_bounds__(256) ln_fold_weights_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, const float* __restrict__ bias,
+                                                              bf16* __restrict__ Wf, float* __restrict__ s_out,
+                                                              float* __restrict__ c_out, int N, int K) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const float* wr = W + (size_t)n * K;
+  bf16* fr = Wf + (size_t)n * K;
+  float s = 0.f, c = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = wr[k];
+    const bf16 f = __float2bfloat16(w * __ldg(gamma + k));
+    fr[k] = f;
+    s += __bfloat162float(f);
+    c = fmaf(__ldg(beta + k), w, c);
+  }
+  s = warp_sum(s);
+  c = warp_sum(c);
+  if (lane == 0) {
+    s_out[n] = s;
+    c_out[n] = c + (bias ? bias[n] : 0.f);
+  }
+}
+
+int launch_ln_fold_weights(const float* W, const float* gamma, const float* beta, const float* bias, bf16* Wf, float* s,
+                           float* c, int N, int K, cudaStream_t st) {
+  ln_fold_weights_kernel<<<(N + 7) / 8, 256, 0, st>>>(W, gamma, beta, bias, Wf, s, c, N, K);
+  TLD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------
 // Patch embedding (denoiser.py:34-45,75-77): one warp per token.
 //   u = 2x2xC patch -> t = W0 u + b0 -> LN(pd) -> e = W3 t + b3 -> LN(D) -> + pos[n]
 // pd <= 64.  The D-wide vector is distributed 4 floats per lane per 128-column group.
