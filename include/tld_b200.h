@@ -203,8 +203,8 @@ TLD_API int tld_train_grad_offset(tld_denoiser* h, const char* key, int64_t* off
  * `ema` may be NULL (ranks other than 0 keep no EMA, tld/train.py:104-106,172).  `step` is the 1-based step count,
  * `grad_scale` multiplies the gradient first (1 = none).  weight_decay is Adam's L2 form (grad += wd * param). */
 TLD_API int tld_adam_ema_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, int64_t n,
-                              float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
-                              float ema_alpha, float grad_scale, void* stream);
+                              double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                              double ema_alpha, double grad_scale, void* stream);
 
 /* ---- backward-pass ops of the training step (autograd through tld/transformer_blocks.py:135-139, driven by
  * tld/train.py:160-170), exported for the parity tests (tests/test_backward_gpu.py) ------------------------------

@@ -79,8 +79,8 @@ PROTOTYPES = {
     "tld_train_prepare": (C.c_int, [C.c_void_p]),
     "tld_train_wait_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "tld_train_grad_offset": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
-    "tld_adam_ema_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,
-                                    C.c_float, C.c_float, C.c_float, C.c_int64, C.c_float, C.c_float, C.c_void_p]),
+    "tld_adam_ema_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double,
+                                    C.c_double, C.c_double, C.c_double, C.c_int64, C.c_double, C.c_double, C.c_void_p]),
     "tld_bwd_cast_transpose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "tld_bwd_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "tld_bwd_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,

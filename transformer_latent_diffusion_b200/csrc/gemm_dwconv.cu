@@ -15,7 +15,8 @@
 //                count land on the peer's cfull barrier, no cluster-scope fence anywhere).
 //   warps 8..23  "conv": four groups of 4 warps, group s takes slab s (= conv tile s) of every tile, so the drain runs a
 //                whole tile ahead and the conv warps never wait for data; warp j of a group produces grid rows 2j, 2j+1: lane = channel pair, a 4-row x 3-column fp32 window slides along x,
-//                packed FFMA2 arithmetic, MUFU-free erf polynomial (dwconv_math.cuh), 128-byte coalesced stores of g.
+//                packed FFMA2 arithmetic, GELU in its logistic form (2 MUFU ex2 + 2 rcp per channel pair, dwconv_math.cuh:
+//                the MUFU unit is idle here and the FMA pipe is the bound), 128-byte coalesced stores of g.
 //   warp 0 / 1 / 2   TMA producer / MMA issuer (leader CTA) / TMEM allocator, exactly as in the plain GEMM.
 //
 // Barriers per CTA: full/empty[stage], tfull/tempty[2] as in the GEMM; cfull[b] (conv tile b written: 4 local drain warps +
@@ -319,7 +320,7 @@ gemm_up_dwconv_gelu_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
               a0 = ffma2(w[dy * 3 + dx], win[(x + dx + 2) % 3][dy], a0);
               a1 = ffma2(w[dy * 3 + dx], win[(x + dx + 2) % 3][dy + 1], a1);
             }
-          const float2 g0 = gelu2(a0), g1 = gelu2(a1);
+          const float2 g0 = gelu2_logistic(a0), g1 = gelu2_logistic(a1);   // MUFU ex2 + rcp: the FMA pipe is this kernel's bound
           *reinterpret_cast<uint32_t*>(out + (size_t)x * N) = pack_bf16x2(g0.x, g0.y);
           *reinterpret_cast<uint32_t*>(out + (size_t)(16 + x) * N) = pack_bf16x2(g1.x, g1.y);
           if (x + 2 < 16) {

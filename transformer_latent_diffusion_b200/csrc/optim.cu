@@ -75,27 +75,28 @@ using namespace tld;
 extern "C" {
 
 TLD_API int tld_adam_ema_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, int64_t n,
-                              float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
-                              float ema_alpha, float grad_scale, void* stream) {
+                              double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                              double ema_alpha, double grad_scale, void* stream) {
   TLD_CHECK(param && grad && exp_avg && exp_avg_sq && n > 0, "tld_adam_ema_step: null argument");
   TLD_CHECK(step >= 1, "tld_adam_ema_step: step counts from 1 (the value AFTER torch's state['step'] += 1)");
   TLD_CHECK(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
               reinterpret_cast<uintptr_t>(exp_avg_sq) | reinterpret_cast<uintptr_t>(ema)) & 15) == 0,
             "tld_adam_ema_step: arenas must be 16-byte aligned");
   AdamArgs a;
-  a.beta1 = beta1;
-  a.beta2 = beta2;
-  a.one_minus_b1 = 1.f - beta1;
-  a.one_minus_b2 = 1.f - beta2;
-  // bias corrections in double, as python floats in torch.optim.Adam (1 - beta ** step)
-  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-  a.step_size = (float)((double)lr / bc1);
+  // hyper-parameters arrive as doubles (python floats) and every derived constant is formed in double before it is rounded
+  // to fp32, exactly as torch does with its scalar arguments: (float)(1 - 0.999) != 1.f - (float)0.999 by 1.3e-5 relative
+  a.beta1 = (float)beta1;
+  a.beta2 = (float)beta2;
+  a.one_minus_b1 = (float)(1.0 - beta1);
+  a.one_minus_b2 = (float)(1.0 - beta2);
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);   // 1 - beta ** step
+  a.step_size = (float)(lr / bc1);
   a.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
-  a.eps = eps;
-  a.weight_decay = weight_decay;
-  a.ema_alpha = ema_alpha;
-  a.one_minus_alpha = 1.f - ema_alpha;
-  a.grad_scale = grad_scale;
+  a.eps = (float)eps;
+  a.weight_decay = (float)weight_decay;
+  a.ema_alpha = (float)ema_alpha;
+  a.one_minus_alpha = (float)(1.0 - ema_alpha);
+  a.grad_scale = (float)grad_scale;
   const long long n4 = n / 4;
   const int tail = int(n - 4 * n4);
   long long want = (n4 + 255) / 256;

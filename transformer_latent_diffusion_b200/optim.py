@@ -158,7 +158,10 @@ class FusedAdamEMA:
         if grp.get("amsgrad"):
             raise _lib.TldError("FusedAdamEMA: amsgrad is not supported")
         if self._arenas is None:
-            self._pending_state = sd      # arenas are created at the first step (they need the device + library handle)
+            # arenas are created at the first step (they need the device + library handle); snapshot now: torch's state_dict()
+            # hands out the live step / moment tensors, which the source optimiser keeps updating in place
+            self._pending_state = {"state": {i: {k: (t.clone() if torch.is_tensor(t) else t) for k, t in st.items()}
+                                             for i, st in sd["state"].items()}, "param_groups": sd["param_groups"]}
             steps = {int(float(st["step"])) for st in sd["state"].values()}
             self.step_count = steps.pop() if len(steps) == 1 else 0
         else:
