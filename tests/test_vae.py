@@ -12,7 +12,7 @@ def _small():
     from transformer_latent_diffusion_b200.vae import AutoencoderKLDecoder
 
     torch.manual_seed(0)
-    m = AutoencoderKLDecoder(block_out=(32, 64, 64, 64))
+    m = AutoencoderKLDecoder(block_out=(32, 64, 64, 64), allow_aten=True)   # widths / CPU tensors the kernels do not take
     for k, p in m.named_parameters():  # exercise affine/bias terms
         if p.ndim == 1:
             p.data.add_(0.1 * torch.randn_like(p))
@@ -116,14 +116,60 @@ def test_decode_gpu_fused_kernels_match_oracle():
     from transformer_latent_diffusion_b200.vae import AutoencoderKLDecoder
 
     torch.manual_seed(1)
-    m = AutoencoderKLDecoder(block_out=(128, 128, 256, 256))
+    m = AutoencoderKLDecoder(block_out=(128, 128, 256, 256))      # allow_aten stays False: every layer must be a library kernel
     for k, p in m.named_parameters():
         if p.ndim == 1:
             p.data.add_(0.1 * torch.randn_like(p))
-    z = torch.randn(2, 4, 8, 8)
+    z = torch.randn(2, 4, 16, 16)
     ref = V.decode({k: v.detach() for k, v in m.state_dict().items()}, z)
     (img,) = m.cuda().to(torch.bfloat16).decode(z.cuda())
+    assert m.own_launches > 100
     assert rel_fro(img, ref) < 8e-2
+
+
+@pytest.mark.gpu
+def test_cuda_tensors_without_a_kernel_raise():
+    """no silent ATen dispatch in the product path (north_star: no multi-backend dispatch): fp32 CUDA tensors, channel counts or
+    map sizes the kernels do not cover raise unless the module was explicitly built with allow_aten=True"""
+    from transformer_latent_diffusion_b200 import _lib
+    from transformer_latent_diffusion_b200.vae import AutoencoderKLDecoder
+
+    m = AutoencoderKLDecoder(block_out=(128, 128, 256, 256)).cuda()
+    (a,) = m.decode(torch.randn(1, 4, 16, 16, device="cuda"))             # fp32 parameters: bf16 operands inside, fp32 out
+    assert a.dtype == torch.float32 and m.own_launches > 50
+    with pytest.raises(_lib.TldError):
+        m.to(torch.bfloat16).decode(torch.randn(1, 4, 8, 8, device="cuda"))   # 64-pixel maps
+    with pytest.raises(_lib.TldError):
+        AutoencoderKLDecoder(block_out=(32, 64, 64, 64)).cuda().to(torch.bfloat16).decode(torch.randn(1, 4, 16, 16, device="cuda"))
+    with pytest.raises(_lib.TldError):
+        AutoencoderKLDecoder(block_out=(128, 128, 256, 256)).decode(torch.randn(1, 4, 16, 16))   # CPU
+
+
+@pytest.mark.gpu
+def test_decode_full_sdxl_width_vs_oracle_with_error_attribution():
+    """The widths bench.py times - (128, 256, 512, 512), one 32x32 latent -> 256x256 image - against the fp32 oracle, with the
+    error attributed: the SAME module run through torch's own bf16 kernels (force_aten) shows how much of the deviation is
+    bf16 arithmetic through ~35 conv / GroupNorm layers with random weights and how much is ours.  PARITY IS UNPINNED (no
+    diffusers here): both are measured against oracle/vae_oracle.py only."""
+    from oracle import vae_oracle as V
+    from transformer_latent_diffusion_b200.vae import AutoencoderKLDecoder
+
+    torch.manual_seed(7)
+    m = AutoencoderKLDecoder(allow_aten=True)
+    for k, p in m.named_parameters():
+        if p.ndim == 1:
+            p.data.add_(0.1 * torch.randn_like(p))
+    z = torch.randn(1, 4, 32, 32)
+    ref = V.decode({k: v.detach() for k, v in m.state_dict().items()}, z)
+    m = m.cuda().to(torch.bfloat16)
+    m.allow_aten = False
+    (mine,) = m.decode(z.cuda())
+    m.allow_aten, m.force_aten = True, True
+    (aten,) = m.decode(z.cuda())
+    e_mine, e_aten = rel_fro(mine, ref), rel_fro(aten, ref)
+    print(f"full-width decode rel-Fro vs fp32 oracle: libtld_b200 {e_mine:.3e}, torch bf16 kernels {e_aten:.3e}")
+    assert e_mine < 3e-2          # measured 2.5e-2 (torch's own bf16 kernels: 3.4e-2): the round-1 bar of 3e-2 holds here
+    assert e_mine < 1.5 * e_aten + 5e-3, (e_mine, e_aten)   # no worse than the stock bf16 graph: the deviation is bf16, not a kernel
 
 
 @pytest.mark.gpu
@@ -171,7 +217,7 @@ def _small_encoder(block_out=(32, 64, 64, 64), seed=0):
     from transformer_latent_diffusion_b200.vae import AutoencoderKLEncoder
 
     torch.manual_seed(seed)
-    m = AutoencoderKLEncoder(block_out=block_out)
+    m = AutoencoderKLEncoder(block_out=block_out, allow_aten=True)
     for k, p in m.named_parameters():
         if p.ndim == 1:
             p.data.add_(0.1 * torch.randn_like(p))
@@ -253,24 +299,25 @@ def test_encode_gpu_matches_oracle_and_roundtrip():
     from transformer_latent_diffusion_b200.vae import AutoencoderKLDecoder
 
     m = _small_encoder(block_out=(128, 128, 256, 256), seed=3)   # widths that take the fused kernels / tcgen05 convs
-    img = torch.rand(3, 3, 64, 64)
+    img = torch.rand(3, 3, 128, 128)
     mean, logvar = V.encode_moments({k: v.detach() for k, v in m.state_dict().items()}, img * 2 - 1)
     torch.backends.cudnn.allow_tf32 = False
-    (p32,) = m.cuda().encode((img * 2 - 1).cuda())
+    (p32,) = m.cuda().encode((img * 2 - 1).cuda())          # fp32 on the GPU = the ATen graph (allow_aten)
     assert rel_fro(p32.mean, mean) < 1e-4 and rel_fro(p32.logvar, logvar) < 1e-4
     mb = m.to(torch.bfloat16)
+    mb.allow_aten = False                                   # bf16: every layer on the library's kernels or it raises
     (pb,) = mb.encode((img * 2 - 1).cuda())
     assert rel_fro(pb.mean, mean) < 8e-2
     assert mb.own_launches > 0, "the encoder did not reach the library kernels"
     # the data-preparation chain of tld/data.py: encode -> quantise (device) -> dequantise -> decode
     lat = encode_image(img, mb, generator=torch.Generator(device="cuda").manual_seed(0), to_cpu=False)
-    assert lat.shape == (3, 4, 8, 8) and lat.dtype == torch.float16 and lat.is_cuda
+    assert lat.shape == (3, 4, 16, 16) and lat.dtype == torch.float16 and lat.is_cuda
     q = quantize_latents(lat)
     back = dequantize_latents(q)
     assert q.dtype == torch.uint8 and (back.float() - lat.float().clip(-20, 20)).abs().max() <= 40.0 / 255 + 1e-2
     dec = AutoencoderKLDecoder(block_out=(128, 128, 256, 256)).cuda().to(torch.bfloat16)
     out = decode_latents(back, dec)
-    assert out.shape == (3, 3, 64, 64) and out.min() >= 0 and out.max() <= 1
+    assert out.shape == (3, 3, 128, 128) and out.min() >= 0 and out.max() <= 1
 
 
 def test_vae_caches_follow_load_state_dict():
@@ -296,7 +343,7 @@ def test_vae_gpu_caches_follow_load_state_dict():
     torch.manual_seed(5)
     m = AutoencoderKLDecoder(block_out=(128, 128, 256, 256)).cuda().to(torch.bfloat16)
     donor = AutoencoderKLDecoder(block_out=(128, 128, 256, 256)).cuda().to(torch.bfloat16)
-    z = torch.randn(2, 4, 8, 8, device="cuda")
+    z = torch.randn(2, 4, 16, 16, device="cuda")
     (before,) = m.decode(z)          # fills the caches with m's initial weights
     m.load_state_dict(donor.state_dict())
     (a,), (b,) = m.decode(z), donor.decode(z)

@@ -8,12 +8,17 @@ diffusers/SDXL-VAE structure with diffusers-compatible ``state_dict`` keys (``po
 ``decoder.conv_out``) so the real checkpoint loads when it is available, and is checked against the independent
 fp32 restatement in ``oracle/vae_oracle.py`` with random weights.
 
-ROUND-1 STATUS: on CUDA/bf16 the GroupNorm(+SiLU) and nearest-2x upsample stages run on hand-written kernels
-(``csrc/vae_kernels.cu`` through ``tld_vae_group_norm`` / ``tld_vae_upsample2x`` / ``tld_vae_add_bias``; in the stock
-ATen path they were 72 % of the decode time) and every 3x3 convolution with >= 64 channels (99.9 % of the decoder's
-FLOPs) runs as an implicit GEMM on the tcgen05 GEMM core (``tld_vae_conv3x3``: 4-D TMA boxes shifted per tap, zero
-fill = padding).  Still on PyTorch library kernels: conv_in (4 input channels), conv_out (3 output channels), the two
-1x1 shortcut convs, post_quant_conv and the single-head mid-block attention (together < 1 % of the FLOPs).
+STATUS: on CUDA/bf16 every layer runs on libtld_b200 kernels.  GroupNorm(+SiLU), nearest-2x upsample and the residual adds
+are hand-written row-wise kernels (``csrc/vae_kernels.cu``); every 3x3 convolution is an implicit GEMM on the tcgen05 GEMM
+core (``tld_vae_conv3x3``: 4-D TMA boxes shifted per tap, zero fill = padding) - the thin ones (conv_in 4 -> 512, conv_out
+128 -> 3, the encoder's 3 -> 128 / 512 -> 8) with their channel count zero-padded to 64; the 1x1 convolutions (shortcuts,
+post_quant_conv / quant_conv) and the q/k/v/out projections of the mid-block attention are plain tcgen05 GEMMs (``tld_op_gemm``
+with the bias epilogue); the encoder's stride-2 convolutions are the stride-1 kernel followed by a 2x sub-sampling.  The ONE
+library call left is the softmax(QK^T)V core of the single 512-wide head of the mid-block attention
+(``F.scaled_dot_product_attention``, < 0.5 % of the FLOPs; the tcgen05 attention kernel of this package is built for 64-wide
+heads).  There is NO silent fallback: a CUDA tensor the kernels do not cover (fp32, odd channel counts, tiny maps) raises
+``TldError``; the plain ATen graph (what the CPU wiring tests and the fp32 oracle cross-check use) only runs when the module
+was built with ``allow_aten=True``.
 """
 from __future__ import annotations
 
@@ -92,9 +97,12 @@ class AutoencoderKLDecoder(nn.Module):
     """``decode(z) -> (image,)`` with the SDXL-VAE decoder topology; z is the latent as the reference passes it
     (already multiplied by ``scale_factor``, tld/diffusion.py:91)."""
 
-    def __init__(self, latent_ch: int = LATENT_CH, block_out: Tuple[int, ...] = BLOCK_OUT, chunk: int = 16):
+    def __init__(self, latent_ch: int = LATENT_CH, block_out: Tuple[int, ...] = BLOCK_OUT, chunk: int = 16,
+                 allow_aten: bool = False):
         super().__init__()
         self.latent_ch, self.block_out, self.chunk = latent_ch, tuple(block_out), chunk
+        self.allow_aten = allow_aten  # test-only: run layers without a libtld_b200 kernel on the plain ATen graph
+        self.force_aten = False       # test-only (needs allow_aten): skip the kernels everywhere = torch's own bf16 graph
         self.own_launches = 0  # libtld_b200 kernels launched by decode() so far (bench.py's gpu_launches)
         self._layout = vae_param_layout(latent_ch, block_out)
         for key, shape in self._layout.items():
@@ -115,13 +123,114 @@ class AutoencoderKLDecoder(nn.Module):
         return mod._parameters[leaf]
 
     # -- building blocks ---------------------------------------------------------------------------------------
+    def _aten(self, what: str, x) -> None:
+        """gate of every ATen fallback: the product path (CUDA, bf16) never dispatches to library kernels silently"""
+        if not self.allow_aten:
+            from . import _lib
+
+            raise _lib.TldError(
+                f"vae: {what} has no libtld_b200 kernel for a {tuple(x.shape)} {x.dtype} tensor on {x.device} (the kernels take "
+                "bf16 CUDA tensors, channel counts that are multiples of 32 with channels/32 a multiple of 4, maps of at least 128 "
+                "pixels); the ATen reference graph only runs on a module built with allow_aten=True (tests)")
+
+    def _compute_dtype(self, w) -> torch.dtype:
+        """On CUDA the module computes with bf16 tensor-core operands and fp32 accumulation whatever the dtype of its
+        parameters (the reference's VAEConfig defaults to fp32 parameters, tld/configs.py:43): the kernels read packed bf16 /
+        fp32 copies of the weights, exactly like the denoiser.  Only a module built with allow_aten=True keeps fp32 (or CPU)
+        tensors on the ATen reference graph."""
+        if w.is_cuda and not (self.allow_aten and w.dtype != torch.bfloat16):
+            return torch.bfloat16
+        return w.dtype
+
+    def _packed(self, key: str, maker):
+        """cache of repacked weights keyed on the parameter's storage / version / device"""
+        w = self._p(key)
+        cache = self.__dict__.setdefault("_wpack_cache", {})
+        sig = (w.data_ptr(), w._version, w.device)
+        ent = cache.get(key)
+        if ent is None or ent[0] != sig:
+            ent = (sig, maker(w.detach()))
+            cache[key] = ent
+        return ent[1]
+
+    def _gemm_bias(self, t, wkey: str, bkey: str, n_pad: int = 0, k_pad: int = 0):
+        """[M, K] bf16 rows (NHWC pixels / tokens) x nn.Linear-or-1x1-conv weight [N, K] + bias on the tcgen05 GEMM
+        (tld_op_gemm, EPI_BIAS_BF16).  n_pad / k_pad: zero-pad the weight to that many outputs / inputs."""
+        from . import _lib
+
+        w = self._p(wkey)
+        N, K = w.shape[0], w.shape[1]
+        Np, Kp = max(N, n_pad), max(K, k_pad)
+
+        def pack(wd):
+            m = torch.zeros(Np, Kp, device=wd.device, dtype=torch.bfloat16)
+            m[:N, :K] = wd.reshape(N, K).to(torch.bfloat16)
+            return m
+
+        wp = self._packed(wkey, pack)
+        bp = self._packed(bkey, lambda b: torch.cat([b.float(), torch.zeros(Np - N, device=b.device)]).contiguous())
+        M = t.shape[0]
+        assert t.shape[1] == Kp and t.is_contiguous() and t.dtype == torch.bfloat16
+        out = torch.empty(M, Np, device=t.device, dtype=torch.bfloat16)
+        _lib.check(_lib.load().tld_op_gemm(1, t.data_ptr(), wp.data_ptr(), M, Np, Kp, out.data_ptr(), bp.data_ptr(),
+                                           _lib.current_stream_ptr(t.device)), "tld_op_gemm")
+        self.own_launches += 1
+        return out
+
+    @staticmethod
+    def _rows(x):
+        """NCHW-shaped channels_last tensor -> its memory as [B*H*W, C] rows"""
+        B, Cc, H, W = x.shape
+        return x.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).reshape(B * H * W, Cc)
+
+    @staticmethod
+    def _from_rows(t, B, H, W):
+        """[B*H*W, C] rows -> NCHW-shaped channels_last tensor (no copy)"""
+        return t.view(B, H, W, t.shape[1]).permute(0, 3, 1, 2)
+
+    def _on_kernels(self, x) -> bool:
+        return x.is_cuda and x.dtype == torch.bfloat16 and not self.force_aten
+
+    def _kernel_map_ok(self, x) -> bool:
+        B, _, H, W = x.shape
+        wb = min(W, 128)
+        return (self._on_kernels(x) and (H * W) % 128 == 0 and 128 % wb == 0 and W % wb == 0 and H % (128 // wb) == 0)
+
+    def _conv3x3_padded(self, x, name):
+        """3x3 conv whose input and / or output channel count is below 64 (conv_in, conv_out): both are zero-padded to 64 and
+        the tcgen05 implicit-GEMM kernel does the rest; the padded output channels are sliced off (they are exact zeros)."""
+        from . import _lib
+
+        w = self._p(name + ".weight")
+        cout, cin = w.shape[0], w.shape[1]
+        cinp, coutp = max(64, -(-cin // 64) * 64), max(64, -(-cout // 64) * 64)
+
+        def pack(wd):
+            m = torch.zeros(coutp, 3, 3, cinp, device=wd.device, dtype=torch.bfloat16)
+            m[:cout, :, :, :cin] = wd.permute(0, 2, 3, 1).to(torch.bfloat16)
+            return m.reshape(coutp, 9 * cinp).contiguous()
+
+        wp = self._packed(name + ".weight", pack)
+        bp = self._packed(name + ".bias", lambda b: torch.cat([b.float(), torch.zeros(coutp - cout, device=b.device)]).contiguous())
+        B, _, H, W = x.shape
+        if x.shape[1] != cinp:   # zero-pad the channels (NHWC memory)
+            xp = torch.zeros((B, H, W, cinp), device=x.device, dtype=x.dtype).permute(0, 3, 1, 2)   # NHWC memory
+            xp[:, :x.shape[1]] = x
+            x = xp
+        x = x.contiguous(memory_format=torch.channels_last)
+        y = torch.empty((B, coutp, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+        _lib.check(_lib.load().tld_vae_conv3x3(x.data_ptr(), wp.data_ptr(), bp.data_ptr(), y.data_ptr(), B, H, W, cinp, coutp,
+                                               _lib.current_stream_ptr(x.device)), "tld_vae_conv3x3")
+        self.own_launches += 1
+        return y   # [B, coutp, H, W]; the caller keeps the padding (next layer is padded too) or slices [:, :cout]
+
     def _own_conv_ok(self, x, name) -> bool:
         """3x3 conv eligible for the tcgen05 implicit-GEMM kernel (tld_vae_conv3x3)"""
         w = self._p(name + ".weight")
         cout, cin, kh, kw = w.shape
         B, _, H, W = x.shape
         wb = min(W, 128)
-        return (x.is_cuda and x.dtype == torch.bfloat16 and kh == 3 and kw == 3 and cin % 64 == 0 and cout % 64 == 0
+        return (self._on_kernels(x) and kh == 3 and kw == 3 and cin % 64 == 0 and cout % 64 == 0
                 and (H * W) % 128 == 0 and 128 % wb == 0 and W % wb == 0 and H % (128 // wb) == 0)
 
     def _conv(self, x, name, pad, bias=True):
@@ -146,7 +255,15 @@ class AutoencoderKLDecoder(nn.Module):
                                                    _lib.current_stream_ptr(x.device)), "tld_vae_conv3x3")
             self.own_launches += 1
             return y
-        return F.conv2d(x, self._p(name + ".weight"), self._p(name + ".bias") if bias else None, padding=pad)
+        w = self._p(name + ".weight")
+        if pad == 1 and bias and w.shape[2] == 3 and self._kernel_map_ok(x):          # thin 3x3: channels padded to 64
+            return self._conv3x3_padded(x, name)[:, :w.shape[0]]
+        if pad == 0 and bias and w.shape[2] == 1 and self._on_kernels(x) and w.shape[1] % 8 == 0 \
+                and w.shape[0] % 32 == 0:                                              # 1x1 conv = GEMM over the pixels
+            B, _, H, W = x.shape
+            return self._from_rows(self._gemm_bias(self._rows(x), name + ".weight", name + ".bias"), B, H, W)
+        self._aten(f"conv {name}", x)
+        return F.conv2d(x, w, self._p(name + ".bias") if bias else None, padding=pad)
 
     def _f32(self, key: str, device) -> torch.Tensor:
         """fp32 copy of a 1-D parameter for the fused kernels (cached per device)"""
@@ -159,11 +276,9 @@ class AutoencoderKLDecoder(nn.Module):
             cache[key] = ent
         return ent[1]
 
-    @staticmethod
-    def _fusable(x) -> bool:
+    def _fusable(self, x) -> bool:
         Cc = x.shape[1]
-        return (x.is_cuda and x.dtype == torch.bfloat16 and Cc % 8 == 0 and Cc <= 512 and 256 % (Cc // 8) == 0
-                and (Cc // GN_GROUPS) % 4 == 0)
+        return (self._on_kernels(x) and Cc % 8 == 0 and Cc <= 512 and 256 % (Cc // 8) == 0 and (Cc // GN_GROUPS) % 4 == 0)
 
     def _group_norm(self, x, name, silu: bool, pre_bias=None):
         """act(GroupNorm(32, eps 1e-6)(x + pre_bias)); fused sm_100a kernels for bf16 channels-last CUDA tensors.
@@ -181,6 +296,7 @@ class AutoencoderKLDecoder(nn.Module):
                 GN_GROUPS, GN_EPS, int(silu), _lib.current_stream_ptr(x.device)), "tld_vae_group_norm")
             self.own_launches += 2  # statistics + apply
             return y
+        self._aten(f"group_norm {name}", x)
         if pre_bias:
             x = x + self._p(pre_bias + ".bias").view(1, -1, 1, 1)
         h = F.group_norm(x, GN_GROUPS, self._p(name + ".weight"), self._p(name + ".bias"), GN_EPS)
@@ -199,10 +315,11 @@ class AutoencoderKLDecoder(nn.Module):
                                                     _lib.current_stream_ptr(h.device)), "tld_vae_add_bias")
             self.own_launches += 1
             return out
+        self._aten("residual add", h)
         return x + h + self._p(bias_of + ".bias").view(1, -1, 1, 1) if bias_of else x + h
 
     def _upsample2x(self, x):
-        if x.is_cuda and x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0:
+        if self._on_kernels(x) and x.shape[1] % 8 == 0:
             from . import _lib
 
             x = x.contiguous(memory_format=torch.channels_last)
@@ -212,6 +329,7 @@ class AutoencoderKLDecoder(nn.Module):
                                                       _lib.current_stream_ptr(x.device)), "tld_vae_upsample2x")
             self.own_launches += 1
             return y
+        self._aten("upsample", x)
         return F.interpolate(x, scale_factor=2.0, mode="nearest")
 
     def _resnet(self, x, name):
@@ -232,6 +350,15 @@ class AutoencoderKLDecoder(nn.Module):
     def _mid_attention(self, x, name):
         B, Cc, H, W = x.shape
         h = self._group_norm(x, name + ".group_norm", False)
+        if self._on_kernels(x) and Cc % 32 == 0:
+            # projections on the tcgen05 GEMM; the softmax(QK^T)V core of this single Cc-wide head is the one library call
+            # of the decoder (module docstring)
+            t = self._rows(h)
+            q, k, v = (self._gemm_bias(t, f"{name}.{p}.weight", f"{name}.{p}.bias").view(B, 1, H * W, Cc) for p in ("to_q", "to_k", "to_v"))
+            o = F.scaled_dot_product_attention(q, k, v).reshape(B * H * W, Cc)
+            o = self._gemm_bias(o.contiguous(), name + ".to_out.0.weight", name + ".to_out.0.bias")
+            return self._add_bias(x, self._from_rows(o, B, H, W))
+        self._aten(f"attention {name}", x)
         t = h.permute(0, 2, 3, 1).reshape(B, H * W, Cc)
         q = F.linear(t, self._p(name + ".to_q.weight"), self._p(name + ".to_q.bias"))
         k = F.linear(t, self._p(name + ".to_k.weight"), self._p(name + ".to_k.bias"))
@@ -241,8 +368,17 @@ class AutoencoderKLDecoder(nn.Module):
         return x + o.reshape(B, H, W, Cc).permute(0, 3, 1, 2)
 
     def _decode_chunk(self, z):
-        x = self._conv(z, "post_quant_conv", 0)
-        x = self._conv(x, "decoder.conv_in", 1)
+        if self._kernel_map_ok(z):
+            # stem on the library's kernels: latent channels zero-padded to 64 once; post_quant_conv (1x1) = one 64x64 GEMM
+            # whose padded outputs are zeros again, which is exactly the padded input conv_in wants
+            B, Cz, H, W = z.shape
+            zp = torch.zeros((B, H, W, 64), device=z.device, dtype=z.dtype).permute(0, 3, 1, 2)   # NHWC memory
+            zp[:, :Cz] = z
+            t = self._gemm_bias(self._rows(zp), "post_quant_conv.weight", "post_quant_conv.bias", n_pad=64, k_pad=64)
+            x = self._conv3x3_padded(self._from_rows(t, B, H, W), "decoder.conv_in")
+        else:
+            x = self._conv(z, "post_quant_conv", 0)
+            x = self._conv(x, "decoder.conv_in", 1)
         x = self._resnet(x, "decoder.mid_block.resnets.0")
         x = self._mid_attention(x, "decoder.mid_block.attentions.0")
         x = self._resnet(x, "decoder.mid_block.resnets.1")
@@ -260,7 +396,7 @@ class AutoencoderKLDecoder(nn.Module):
     def decode(self, z: torch.Tensor):
         """z [B,4,h,w] -> (image [B,3,8h,8w],) in z's dtype; processed in chunks of ``self.chunk`` images."""
         w = self._p("decoder.conv_in.weight")
-        zz = z.to(device=w.device, dtype=w.dtype)
+        zz = z.to(device=w.device, dtype=self._compute_dtype(w))
         if zz.is_cuda:
             zz = zz.contiguous(memory_format=torch.channels_last)
         outs = [self._decode_chunk(zz[i:i + self.chunk]) for i in range(0, zz.shape[0], self.chunk)]
@@ -363,9 +499,12 @@ class AutoencoderKLEncoder(AutoencoderKLDecoder):
     (tld/data.py:38-40).  Inherits the decoder's kernels-backed building blocks; only the parameter layout and the
     forward wiring differ."""
 
-    def __init__(self, latent_ch: int = LATENT_CH, block_out: Tuple[int, ...] = BLOCK_OUT, chunk: int = 16):
+    def __init__(self, latent_ch: int = LATENT_CH, block_out: Tuple[int, ...] = BLOCK_OUT, chunk: int = 16,
+                 allow_aten: bool = False):
         nn.Module.__init__(self)
         self.latent_ch, self.block_out, self.chunk = latent_ch, tuple(block_out), chunk
+        self.allow_aten = allow_aten
+        self.force_aten = False
         self.own_launches = 0
         self._layout = vae_encoder_param_layout(latent_ch, block_out)
         for key, shape in self._layout.items():
@@ -379,7 +518,12 @@ class AutoencoderKLEncoder(AutoencoderKLDecoder):
             _attach(self, key, t)
 
     def _downsample(self, x, name):
-        # diffusers Downsample2D(padding=0): pad right/bottom by one pixel, 3x3 conv with stride 2
+        # diffusers Downsample2D(padding=0): pad right/bottom by one pixel, 3x3 conv with stride 2:
+        #   out[y, x] = sum_k w[ky, kx] in[2y + ky, 2x + kx]  ==  the stride-1 'same' convolution sampled at (2y+1, 2x+1)
+        # (its zero padding at the bottom / right edge is the same padded pixel) -> the tcgen05 kernel + a 2x sub-sampling
+        if self._own_conv_ok(x, name):
+            return self._conv(x, name, 1)[:, :, 1::2, 1::2].contiguous(memory_format=torch.channels_last)
+        self._aten(f"downsample {name}", x)
         return F.conv2d(F.pad(x, (0, 1, 0, 1)), self._p(name + ".weight"), self._p(name + ".bias"), stride=2)
 
     def _encode_chunk(self, x):
@@ -394,6 +538,12 @@ class AutoencoderKLEncoder(AutoencoderKLDecoder):
         h = self._mid_attention(h, "encoder.mid_block.attentions.0")
         h = self._resnet(h, "encoder.mid_block.resnets.1")
         h = self._group_norm(h, "encoder.conv_norm_out", True)
+        if self._kernel_map_ok(h) and self._own_conv_ok(h, "encoder.mid_block.resnets.1.conv2"):
+            # conv_out (512 -> 8) with its outputs zero-padded to 64, quant_conv (1x1, 8 -> 8) as one 64x64 GEMM on those rows
+            B, _, H, W = h.shape
+            y = self._conv3x3_padded(h, "encoder.conv_out")
+            t = self._gemm_bias(self._rows(y), "quant_conv.weight", "quant_conv.bias", n_pad=64, k_pad=64)
+            return self._from_rows(t, B, H, W)[:, :2 * self.latent_ch]
         h = self._conv(h, "encoder.conv_out", 1)
         return self._conv(h, "quant_conv", 0)
 
@@ -401,7 +551,7 @@ class AutoencoderKLEncoder(AutoencoderKLDecoder):
     def encode(self, x: torch.Tensor, return_dict: bool = False):
         """x [B,3,H,W] in [-1,1] -> (DiagonalGaussian over [B,4,H/8,W/8],); processed in chunks of ``self.chunk`` images."""
         w = self._p("encoder.conv_in.weight")
-        xx = x.to(device=w.device, dtype=w.dtype)
+        xx = x.to(device=w.device, dtype=self._compute_dtype(w))
         if xx.is_cuda:
             xx = xx.contiguous(memory_format=torch.channels_last)
         moments = torch.cat([self._encode_chunk(xx[i:i + self.chunk]) for i in range(0, xx.shape[0], self.chunk)])
