@@ -38,7 +38,7 @@ typedef struct tld_config {
   int32_t image_size;       /* latent H = W                         */
   int32_t noise_embed_dims; /* sinusoidal embedding width E         */
   int32_t patch_size;
-  int32_t embed_dim;        /* D, multiple of 128, heads = D/64     */
+  int32_t embed_dim;        /* D, multiple of 64, heads = D/64      */
   int32_t n_layers;
   int32_t text_emb_size;
   int32_t mlp_multiplier;

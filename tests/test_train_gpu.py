@@ -186,6 +186,6 @@ def test_adam_ema_kernel_vs_torch(n, wd, with_ema):
     assert torch.allclose(m, sd["exp_avg"], rtol=1e-4, atol=1e-6 * float(m.abs().max()))   # cancellation near zero: absolute bound
     assert torch.allclose(p, p_ref.detach(), rtol=0, atol=2e-7 * 5), float((p - p_ref.detach()).abs().max())
     if with_ema:
-        assert torch.allclose(ema, ema_ref, rtol=0, atol=1e-6)
+        assert torch.allclose(ema, ema_ref, rtol=3e-6, atol=1e-6)
     else:
         assert torch.equal(ema, p0)

@@ -9,6 +9,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce after the backward instead of overlapped with it")
+    ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam(fused=True) + update_ema instead of FusedAdamEMA")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -21,7 +22,12 @@ def main():
     m = Denoiser(32, 256, 2, 768, 0, 12).cuda().train()
     m.overlap_grad_allreduce = not a.no_overlap
     ema = copy.deepcopy(m)
-    opt = torch.optim.Adam(m.parameters(), lr=3e-4, fused=True)
+    if a.torch_adam:
+        opt = torch.optim.Adam(m.parameters(), lr=3e-4, fused=True)
+    else:
+        from transformer_latent_diffusion_b200.optim import FusedAdamEMA
+        opt = FusedAdamEMA(m, lr=3e-4, ema_model=ema, alpha=0.999)
+        m.grad_views = True
     B = a.batch
     g = torch.Generator(device="cuda").manual_seed(local)
     x = torch.randn(B, 4, 32, 32, device="cuda", generator=g) * 8
@@ -32,7 +38,8 @@ def main():
         mask = torch.rand(B, device="cuda") < 0.15
         xs, xn, sg, lab = noise_batch(x, y, sigma, eps, mask, 8.0)
         loss = train_step(m, opt, xs, xn, sg, lab)
-        update_ema(ema, m, 0.999)
+        if a.torch_adam:
+            update_ema(ema, m, 0.999)
         return loss
     for _ in range(3):
         l = one()

@@ -32,8 +32,8 @@ class DenoiserConfig:
 
     def check_b200_support(self) -> None:
         """Raise ValueError for shapes the sm_100a kernels do not cover (see DESIGN.md 'limits')."""
-        if self.embed_dim % 128 or not 128 <= self.embed_dim <= 1024:
-            raise ValueError("embed_dim must be a multiple of 128 in [128, 1024]")
+        if self.embed_dim % 64 or not 64 <= self.embed_dim <= 1024:
+            raise ValueError("embed_dim must be a multiple of 64 in [64, 1024] (training: a multiple of 128)")
         if self.image_size % self.patch_size:
             raise ValueError("image_size must be divisible by patch_size")
         if ((self.image_size // self.patch_size) ** 2) % 64:

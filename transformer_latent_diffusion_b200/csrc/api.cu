@@ -415,8 +415,8 @@ int tld_denoiser_create(const tld_config* cfg, int device, tld_denoiser** out) {
   TLD_CUDA_OK(cudaGetDeviceProperties(&prop, device));
   TLD_CHECK(prop.major == 10, "tld_denoiser_create: kernels are built for sm_100a (B200) only, found sm_" +
                                   std::to_string(prop.major) + std::to_string(prop.minor));
-  TLD_CHECK(cfg->embed_dim % 128 == 0 && cfg->embed_dim >= 128 && cfg->embed_dim <= 1024,
-            "embed_dim must be a multiple of 128 in [128,1024]");
+  TLD_CHECK(cfg->embed_dim % 64 == 0 && cfg->embed_dim >= 64 && cfg->embed_dim <= 1024,
+            "embed_dim must be a multiple of 64 in [64,1024] (heads = embed_dim / 64, transformer_blocks.py:126-129)");
   TLD_CHECK(cfg->patch_size > 0 && cfg->image_size % cfg->patch_size == 0, "image_size must be divisible by patch_size");
   const int G = cfg->image_size / cfg->patch_size;
   TLD_CHECK((G * G) % 64 == 0, "tokens per sample ((image_size/patch_size)^2) must be a multiple of 64");

@@ -67,10 +67,46 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __rest
   }
 }
 
+// embed_dim = 64 x odd (the reference takes any multiple of 64: heads = D // 64, transformer_blocks.py:126-129): same scheme
+// with scalar lanes, column c = lane + 32 j (coalesced 128-byte warp accesses), row held in registers.
+__global__ void __launch_bounds__(256) layernorm_bf16_generic_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta, bf16* __restrict__ y,
+                                                                     int rows, int D) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * D;
+  const int n = D / 32;   // <= 32
+  float v[32];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    v[j] = j < n ? xr[lane + 32 * j] : 0.f;
+    s += v[j];
+  }
+  const float mu = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (j < n) q += (v[j] - mu) * (v[j] - mu);
+  const float rstd = rsqrtf(warp_sum(q) / D + LN_EPS);
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (j < n) {
+      const int c = lane + 32 * j;
+      y[(size_t)row * D + c] = __float2bfloat16((v[j] - mu) * rstd * __ldg(gamma + c) + __ldg(beta + c));
+    }
+}
+
 int launch_layernorm_bf16(const float* x, const float* gamma, const float* beta, bf16* y, int rows, int D,
                           cudaStream_t st) {
-  TLD_CHECK(D % 128 == 0 && D >= 128 && D <= 1024, "layernorm: embed_dim must be a multiple of 128 in [128,1024]");
+  TLD_CHECK(D % 64 == 0 && D >= 64 && D <= 1024, "layernorm: embed_dim must be a multiple of 64 in [64,1024]");
   const int grid = (rows + 7) / 8;
+  if (D % 128 != 0) {
+    layernorm_bf16_generic_kernel<<<grid, 256, 0, st>>>(x, gamma, beta, y, rows, D);
+    TLD_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   switch (D / 128) {
 #define LN_CASE(V) \
   case V: if (launch_pdl(layernorm_bf16_kernel<V>, dim3(grid), dim3(256), 0, st, x, gamma, beta, y, rows)) return 1; break;
@@ -262,10 +298,88 @@ __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ x,
   }
 }
 
+// embed_dim = 64 x odd: the same computation with scalar lanes (column c = lane + 32 j); inference only (no EmbedSave)
+__global__ void __launch_bounds__(256) embed_generic_kernel(const float* __restrict__ x, int Bx, int Bout, int C, int img,
+                                                            int patch, int D, EmbedW w, float* __restrict__ out) {
+  __shared__ float s_t[8][64];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = img / patch, N = g * g, pd = C * patch * patch;
+  const long long tok = (long long)blockIdx.x * 8 + wib;
+  if (tok >= (long long)Bout * N) return;
+  const int b = int(tok / N), n = int(tok % N);
+  const int gy = n / g, gx = n % g;
+  const float* xb = x + (size_t)(b % Bx) * C * img * img;
+  float* t = s_t[wib];
+  for (int i = lane; i < pd; i += 32) {
+    const int c = i / (patch * patch), p1 = (i / patch) % patch, p2 = i % patch;
+    t[i] = xb[(size_t)c * img * img + (size_t)(gy * patch + p1) * img + gx * patch + p2];
+  }
+  __syncwarp();
+  float conv[2] = {0.f, 0.f};
+  float s = 0.f;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int o = lane + 32 * r;
+    if (o < pd) {
+      float acc = w.conv_b[o];
+      for (int i = 0; i < pd; ++i) acc += w.conv_w[o * pd + i] * t[i];
+      conv[r] = acc;
+      s += acc;
+    }
+  }
+  const float mu1 = warp_sum(s) / pd;
+  float q = 0.f;
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+    if (lane + 32 * r < pd) q += (conv[r] - mu1) * (conv[r] - mu1);
+  const float rstd1 = rsqrtf(warp_sum(q) / pd + LN_EPS);
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int o = lane + 32 * r;
+    if (o < pd) t[o] = (conv[r] - mu1) * rstd1 * w.ln1_w[o] + w.ln1_b[o];
+  }
+  __syncwarp();
+  const int nj = D / 32;   // <= 32
+  float e[32];
+  float s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    e[j] = 0.f;
+    if (j < nj) {
+      const int c = lane + 32 * j;
+      float acc = __ldg(w.lin_b + c);
+      for (int i = 0; i < pd; ++i) acc += __ldg(w.lin_wT + (size_t)i * D + c) * t[i];
+      e[j] = acc;
+      s2 += acc;
+    }
+  }
+  const float mu2 = warp_sum(s2) / D;
+  float q2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (j < nj) q2 += (e[j] - mu2) * (e[j] - mu2);
+  const float rstd2 = rsqrtf(warp_sum(q2) / D + LN_EPS);
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (j < nj) {
+      const int c = lane + 32 * j;
+      out[(size_t)tok * D + c] = (e[j] - mu2) * rstd2 * __ldg(w.ln2_w + c) + __ldg(w.ln2_b + c) + __ldg(w.pos + (size_t)n * D + c);
+    }
+}
+
 int launch_embed(const float* x, int Bx, int Bout, int C, int img, int patch, int D, const EmbedW& w, float* out,
                  cudaStream_t st, const EmbedSave* svp) {
   const EmbedSave sv = svp ? *svp : EmbedSave{nullptr, nullptr, nullptr, nullptr};
-  TLD_CHECK(D % 128 == 0 && D >= 128 && D <= 1024, "embed: embed_dim must be a multiple of 128 in [128,1024]");
+  TLD_CHECK(D % 64 == 0 && D >= 64 && D <= 1024, "embed: embed_dim must be a multiple of 64 in [64,1024]");
+  if (D % 128 != 0) {
+    TLD_CHECK(svp == nullptr, "embed: the training path needs embed_dim % 128 == 0");
+    TLD_CHECK(C * patch * patch <= 64 && img % patch == 0, "embed: bad patch geometry");
+    const long long toks_g = (long long)Bout * (img / patch) * (img / patch);
+    embed_generic_kernel<<<int((toks_g + 7) / 8), 256, 0, st>>>(x, Bx, Bout, C, img, patch, D, w, out);
+    TLD_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   TLD_CHECK(C * patch * patch <= 64, "embed: patch_dim (n_channels*patch^2) must be <= 64");
   TLD_CHECK(img % patch == 0, "embed: image_size must be divisible by patch_size");
   const long long toks = (long long)Bout * (img / patch) * (img / patch);

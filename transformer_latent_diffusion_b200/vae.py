@@ -97,7 +97,7 @@ class AutoencoderKLDecoder(nn.Module):
     """``decode(z) -> (image,)`` with the SDXL-VAE decoder topology; z is the latent as the reference passes it
     (already multiplied by ``scale_factor``, tld/diffusion.py:91)."""
 
-    def __init__(self, latent_ch: int = LATENT_CH, block_out: Tuple[int, ...] = BLOCK_OUT, chunk: int = 16,
+    def __init__(self, latent_ch: int = LATENT_CH, block_out: Tuple[int, ...] = BLOCK_OUT, chunk: int = 32,
                  allow_aten: bool = False):
         super().__init__()
         self.latent_ch, self.block_out, self.chunk = latent_ch, tuple(block_out), chunk
@@ -499,7 +499,7 @@ class AutoencoderKLEncoder(AutoencoderKLDecoder):
     (tld/data.py:38-40).  Inherits the decoder's kernels-backed building blocks; only the parameter layout and the
     forward wiring differ."""
 
-    def __init__(self, latent_ch: int = LATENT_CH, block_out: Tuple[int, ...] = BLOCK_OUT, chunk: int = 16,
+    def __init__(self, latent_ch: int = LATENT_CH, block_out: Tuple[int, ...] = BLOCK_OUT, chunk: int = 32,
                  allow_aten: bool = False):
         nn.Module.__init__(self)
         self.latent_ch, self.block_out, self.chunk = latent_ch, tuple(block_out), chunk
