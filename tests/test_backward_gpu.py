@@ -98,7 +98,8 @@ def test_cross_attention_backward(lib, B, n_tok, D):
     assert rel_fro(d0, kv0.grad) < 1e-4 and rel_fro(d1, kv1.grad) < 1e-4
 
 
-@pytest.mark.parametrize("B,n_tok,D", [(1, 64, 128), (2, 256, 128), (2, 256, 768), (3, 128, 256)])
+@pytest.mark.parametrize("B,n_tok,D", [(1, 64, 128), (2, 256, 128), (2, 256, 768), (3, 128, 256),
+                                       (2, 512, 128), (1, 1024, 192), (1, 4096, 64)])   # > 256 tokens: the key-tiled kernels
 def test_self_attention_backward(lib, B, n_tok, D):
     g = torch.Generator(device="cuda").manual_seed(n_tok * 3 + D)
     T, H = B * n_tok, D // 64

@@ -31,7 +31,8 @@ def _model(cfg, sd):
     return m.cuda().train()
 
 
-@pytest.mark.parametrize("img,D,L,B", [(16, 128, 2, 4), (32, 256, 1, 3), (32, 768, 2, 2)])
+@pytest.mark.parametrize("img,D,L,B", [(16, 128, 2, 4), (32, 256, 1, 3), (32, 768, 2, 2),
+                                       (64, 128, 1, 2)])   # 1024 tokens per sample: the 512-px model's training path
 def test_parameter_gradients_match_oracle(img, D, L, B):
     cfg = O.OracleCfg(image_size=img, embed_dim=D, n_layers=L)
     sd = O.synth_state_dict(cfg, 17)

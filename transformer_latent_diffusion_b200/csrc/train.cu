@@ -231,7 +231,7 @@ TLD_API int tld_train_forward(tld_denoiser* h, const float* x, const float* nois
                               int batch, void* stream) {
   TLD_CHECK(h && x && noise_level && label && out && batch > 0, "tld_train_forward: bad argument");
   TLD_CHECK(tld_denoiser_missing_params(h) == 0, "tld_train_forward: parameters missing");
-  TLD_CHECK(h->N <= 256, "tld_train_forward: the attention backward supports at most 256 tokens per sample");
+  TLD_CHECK(h->N <= 256 || h->N % 256 == 0, "tld_train_forward: the attention backward needs <= 256 tokens per sample or a multiple of 256");
   TLD_CHECK(h->D % 128 == 0, "tld_train_forward: the training kernels need embed_dim % 128 == 0");
   TLD_CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -145,8 +145,11 @@ def _overlapped_allreduce(module, handle, dev) -> bool:
 
 def denoiser_autograd_forward(module, x: Tensor, noise_level: Tensor, label: Tensor) -> Tensor:
     """Differentiable ``Denoiser.forward`` (w.r.t. the parameters; the latents/labels get no gradient)."""
-    if module.image_size // module.patch_size > 16:
-        raise _lib.TldError("training path supports up to 256 tokens per sample (image_size/patch_size <= 16)")
+    n_tok = (module.image_size // module.patch_size) ** 2
+    if n_tok > 256 and n_tok % 256:
+        raise _lib.TldError("training path: tokens per sample must be <= 256 or a multiple of 256")
+    if module.embed_dim % 128:
+        raise _lib.TldError("training path: embed_dim must be a multiple of 128")
     params = [p for _, p in module.named_parameters()]
     return _DenoiserFn.apply(module, x, noise_level, label, *params)
 
