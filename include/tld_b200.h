@@ -160,6 +160,11 @@ TLD_API int tld_vae_add_bias(const uint16_t* x, const uint16_t* h, const float* 
  * out NHWC bf16 [batch,h,w,cout]; cin,cout multiples of 64, h*w multiple of 128. */
 TLD_API int tld_vae_conv3x3(const uint16_t* x, const uint16_t* w, const float* bias, uint16_t* out, int batch, int h,
                             int w_px, int cin, int cout, void* stream);
+/* decoder.conv_out (3x3 'same', 128 -> 3 channels): an HBM-bound direct convolution on the CUDA cores (nothing for a tensor core
+ * to do with 3 output channels).  x NHWC bf16 [batch,h,w,128] (device); w_host [3,128,3,3] and b_host [3] are HOST fp32 arrays
+ * (the 3456 weights travel in the kernel-parameter constant bank); out fp32 NCHW [batch,3,h,w] (device) = the final image. */
+TLD_API int tld_vae_conv_out3(const uint16_t* x, const float* w_host, const float* b_host, float* out, int batch, int h, int w,
+                              void* stream);
 /* nearest-neighbour 2x upsample, NHWC bf16: x [batch,h,w,channels] -> y [batch,2h,2w,channels] */
 TLD_API int tld_vae_upsample2x(const uint16_t* x, uint16_t* y, int batch, int h, int w, int channels, void* stream);
 /* Image post-processing on the device (tld/diffusion.py:185, tld/train.py:36): img [batch,3,h,w] in [-1,1] (fp32, or bf16 when

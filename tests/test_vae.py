@@ -351,3 +351,23 @@ def test_vae_gpu_caches_follow_load_state_dict():
     # (two instances go through cuDNN/cuBLAS for conv_in/conv_out/attention: algorithm choices differ at the bf16 level,
     #  a few 1e-3 .. 1e-2 after 30 layers; unrelated weights differ by O(1))
     assert rel_fro(a, b) < 5e-2 and rel_fro(a, before) > 0.3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W", [(1, 8, 32), (2, 64, 64), (3, 40, 72), (1, 256, 256)])
+def test_conv_out3_direct_kernel(B, H, W):
+    """decoder.conv_out (128 -> 3, 3x3 'same') as the HBM-bound direct convolution with constant-bank weights, incl. ragged tiles"""
+    from transformer_latent_diffusion_b200 import _lib
+
+    g = torch.Generator(device="cuda").manual_seed(B * H + W)
+    x = torch.randn(B, 128, H, W, device="cuda", generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+    w = torch.randn(3, 128, 3, 3, device="cuda", generator=g) / 34.0
+    bias = torch.randn(3, device="cuda", generator=g)
+    ref = torch.nn.functional.conv2d(x.float(), w, bias, padding=1)
+    out = torch.full((B, 3, H, W), float("nan"), device="cuda")
+    wh, bh = w.cpu().contiguous(), bias.cpu().contiguous()
+    _lib.check(_lib.load().tld_vae_conv_out3(x.data_ptr(), wh.data_ptr(), bh.data_ptr(), out.data_ptr(), B, H, W,
+                                             torch.cuda.current_stream().cuda_stream), "conv_out3")
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert rel_fro(out, ref) < 1e-5

@@ -390,6 +390,20 @@ class AutoencoderKLDecoder(nn.Module):
                 x = self._upsample2x(x)
                 x = self._conv(x, f"decoder.up_blocks.{i}.upsamplers.0.conv", 1)
         x = self._group_norm(x, "decoder.conv_norm_out", True)
+        w = self._p("decoder.conv_out.weight")
+        if self._on_kernels(x) and tuple(w.shape[:2]) == (3, 128):
+            # 128 -> 3 channels at full resolution: HBM-bound direct convolution (tld_vae_conv_out3), fp32 NCHW image out
+            from . import _lib
+
+            wh = self._packed("decoder.conv_out.weight", lambda t: t.float().cpu().contiguous())   # host copies: kernel parameters
+            bh = self._packed("decoder.conv_out.bias", lambda t: t.float().cpu().contiguous())
+            x = x.contiguous(memory_format=torch.channels_last)
+            B, _, H, W = x.shape
+            y = torch.empty((B, 3, H, W), device=x.device, dtype=torch.float32)
+            _lib.check(_lib.load().tld_vae_conv_out3(x.data_ptr(), wh.data_ptr(), bh.data_ptr(), y.data_ptr(), B, H, W,
+                                                     _lib.current_stream_ptr(x.device)), "tld_vae_conv_out3")
+            self.own_launches += 1
+            return y
         return self._conv(x, "decoder.conv_out", 1)
 
     @torch.no_grad()
