@@ -145,7 +145,7 @@ int launch_conv3x3(const bf16* x, const bf16* w, const float* bias, bf16* out, i
 // MLPSepConv front half fused (gemm_dwconv.cu): g = GELU(dwconv3x3(A W^T [LayerNorm-folded] + c) + dw_b) for 16x16-token samples
 int launch_gemm_up_dwconv_gelu(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const float* col_c,
                                const float* col_s, const float2* row_part, int n_part, float ln_eps, const float* dw_w9,
-                               const float* dw_b, bf16* out, cudaStream_t st);
+                               const float* dw_b, bf16* out, cudaStream_t st, bf16* hid_out = nullptr);
 void set_gemm_ctas(int v);  // 0 auto, 1 single-CTA tiles, 2 CTA-pair tiles (experiments / tests)
 
 // 2-D row-major TMA descriptor (bf16 or fp32), box = [box_rows, 128 bytes], 128B swizzle (gemm.cu)

@@ -49,6 +49,7 @@ struct FusedUpArgs {
   const float* dw_w9;      // [9, N] depthwise taps, tap-major
   const float* dw_b;       // [N]
   bf16* out;               // [M, N] g
+  bf16* hid_out;           // optional [M, N]: the pre-conv hidden tensor as well (training keeps it for the backward)
 };
 
 constexpr int FU_BN = 256, FU_BK = 64, FU_STAGES = 4, FU_THREADS = 768;
@@ -257,6 +258,11 @@ gemm_up_dwconv_gelu_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             sts_v4(own + (((half * 4 + j) ^ (lane & 7)) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          if (ep.hid_out) {   // training: the backward differentiates through the conv and needs its input
+            uint4* hp = reinterpret_cast<uint4*>(ep.hid_out + (size_t)(m0 + et) * N + n0 + s * 64 + half * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hp[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
           if (push) {   // 16 lanes x 128 B per slab = the 2 KB the peer's cfull barrier expects
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -350,7 +356,7 @@ gemm_up_dwconv_gelu_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
 // g[M, N] = GELU(dwconv3x3(A[M,K] W[N,K]^T (LN-folded) + c) + dw_b), M = batch * 256 tokens (16 x 16 grid per sample)
 int launch_gemm_up_dwconv_gelu(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const float* col_c,
                                const float* col_s, const float2* row_part, int n_part, float ln_eps, const float* dw_w9,
-                               const float* dw_b, bf16* out, cudaStream_t st) {
+                               const float* dw_b, bf16* out, cudaStream_t st, bf16* hid_out) {
   TLD_CHECK(M > 0 && M % 256 == 0, "gemm_up_dwconv: rows must be whole 16x16-token samples (M % 256 == 0)");
   TLD_CHECK(N > 0 && N % FU_BN == 0, "gemm_up_dwconv: hidden width must be a multiple of 256");
   TLD_CHECK(K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm_up_dwconv: K/lda/ldw must be multiples of 8");
@@ -374,6 +380,7 @@ int launch_gemm_up_dwconv_gelu(const bf16* A, int lda, const bf16* W, int ldw, i
   ep.dw_w9 = dw_w9;
   ep.dw_b = dw_b;
   ep.out = out;
+  ep.hid_out = hid_out;
   auto kern = gemm_up_dwconv_gelu_kernel;
   static bool attr_set = false;
   if (!attr_set) {

@@ -95,6 +95,7 @@ struct tld_denoiser {
   struct TrainLayer {
     float *xs0, *xs1, *xs2;        // residual stream before self-attn / cross-attn / MLP, fp32 [T,D]
     bf16 *qkv, *hid, *hid2;        // saved GEMM outputs
+    bf16 *xn0, *xn1, *xn2;         // saved LayerNorm outputs (norm1/2/3): the A operands of the wgrad GEMMs, not recomputed
   };
   std::vector<TrainLayer> tl;
   int train_batch = 0;

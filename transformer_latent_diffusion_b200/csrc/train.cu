@@ -205,7 +205,8 @@ static int ensure_train(tld_denoiser* h, int B) {
   for (int l = 0; l < L; ++l) {
     auto& t = h->tl[l];
     if (talloc(h, &t.xs0, T * D) || talloc(h, &t.xs1, T * D) || talloc(h, &t.xs2, T * D) || talloc(h, &t.qkv, T * 3 * D) ||
-        talloc(h, &t.hid, T * H4) || talloc(h, &t.hid2, T * H4))
+        talloc(h, &t.hid, T * H4) || talloc(h, &t.hid2, T * H4) || talloc(h, &t.xn0, T * D) || talloc(h, &t.xn1, T * D) ||
+        talloc(h, &t.xn2, T * D))
       return 1;
   }
   const long long kvs = 2LL * L * D;
@@ -257,17 +258,23 @@ TLD_API int tld_train_forward(tld_denoiser* h, const float* x, const float* nois
     const auto& ly = h->layers[l];
     auto& t = h->tl[l];
     TLD_CUDA_OK(cudaMemcpyAsync(t.xs0, h->x_res, xbytes, cudaMemcpyDeviceToDevice, st));
-    if (launch_layernorm_bf16(h->x_res, ly.ln1w, ly.ln1b, h->xn, T, D, st)) return 1;
-    if (launch_gemm(EPI_BF16, h->xn, D, ly.wqkv, D, T, 3 * D, D, t.qkv, 3 * D, nullptr, nullptr, st)) return 1;
+    if (launch_layernorm_bf16(h->x_res, ly.ln1w, ly.ln1b, t.xn0, T, D, st)) return 1;   // kept: A operand of the qkv wgrad
+    if (launch_gemm(EPI_BF16, t.xn0, D, ly.wqkv, D, T, 3 * D, D, t.qkv, 3 * D, nullptr, nullptr, st)) return 1;
     if (launch_self_attention(t.qkv, h->x_res, B, N, D, st, 0)) return 1;
     TLD_CUDA_OK(cudaMemcpyAsync(t.xs1, h->x_res, xbytes, cudaMemcpyDeviceToDevice, st));
-    if (launch_layernorm_bf16(h->x_res, ly.ln2w, ly.ln2b, h->xn, T, D, st)) return 1;
+    if (launch_layernorm_bf16(h->x_res, ly.ln2w, ly.ln2b, t.xn1, T, D, st)) return 1;
     XattnArgs xa{h->kv + (size_t)l * 2 * D, h->kv + (size_t)B * kvs + (size_t)l * 2 * D, kvs, kvs, nullptr, N, D};
-    if (launch_gemm(EPI_XATTN_RESID_F32, h->xn, D, ly.wq, D, T, D, D, h->x_res, D, nullptr, &xa, st)) return 1;
+    if (launch_gemm(EPI_XATTN_RESID_F32, t.xn1, D, ly.wq, D, T, D, D, h->x_res, D, nullptr, &xa, st)) return 1;
     TLD_CUDA_OK(cudaMemcpyAsync(t.xs2, h->x_res, xbytes, cudaMemcpyDeviceToDevice, st));
-    if (launch_layernorm_bf16(h->x_res, ly.ln3w, ly.ln3b, h->xn, T, D, st)) return 1;
-    if (launch_gemm(EPI_BIAS_BF16, h->xn, D, ly.wup, D, T, H4, D, t.hid, H4, ly.bup, nullptr, st)) return 1;
-    if (launch_dwconv_gelu(t.hid, ly.dww9, ly.dwb, t.hid2, B, h->G, H4, st)) return 1;
+    if (launch_layernorm_bf16(h->x_res, ly.ln3w, ly.ln3b, t.xn2, T, D, st)) return 1;
+    if (h->G == 16 && H4 % 256 == 0) {   // up-projection + depthwise conv + GELU in one kernel, hidden tensor stored as well
+      if (launch_gemm_up_dwconv_gelu(t.xn2, D, ly.wup, D, T, H4, D, ly.bup, nullptr, nullptr, 0, 1e-5f, ly.dww9, ly.dwb, t.hid2, st,
+                                     t.hid))
+        return 1;
+    } else {
+      if (launch_gemm(EPI_BIAS_BF16, t.xn2, D, ly.wup, D, T, H4, D, t.hid, H4, ly.bup, nullptr, st)) return 1;
+      if (launch_dwconv_gelu(t.hid, ly.dww9, ly.dwb, t.hid2, B, h->G, H4, st)) return 1;
+    }
     if (launch_gemm(EPI_BIAS_RESID_F32, t.hid2, H4, ly.wdown, H4, T, D, H4, h->x_res, D, ly.bdown, nullptr, st)) return 1;
   }
   return launch_outproj(h->x_res, h->out_w, h->out_b, out, B, h->C, h->img, h->patch, D, st);
@@ -322,23 +329,20 @@ TLD_API int tld_train_backward(tld_denoiser* h, const float* d_pred, int batch, 
     transpose_f32_small_kernel<<<blocks(9LL * H4), 256, 0, st>>>(dw9, G(h, b + "mlp.mlp.1.weight"), 9, H4);  // [9,C] -> [C,9]
     TLD_CUDA_OK(cudaGetLastError());
     if (launch_colsum_bf16(h->t_big, G(h, b + "mlp.mlp.0.bias"), T, H4, 0, st)) return 1;
-    if (launch_layernorm_bf16(t.xs2, ly.ln3w, ly.ln3b, h->xn, T, D, st)) return 1;                  // recompute LN3(x2)
-    if (launch_gemm_mn(EPI_F32, h->t_big, H4, h->xn, D, H4, D, T, G(h, b + "mlp.mlp.0.weight"), D, st)) return 1;  // d_hid^T xn
+    if (launch_gemm_mn(EPI_F32, h->t_big, H4, t.xn2, D, H4, D, T, G(h, b + "mlp.mlp.0.weight"), D, st)) return 1;  // d_hid^T LN3(x2)
     if (launch_gemm_nn(EPI_F32, h->t_big, H4, ly.wup, D, T, D, H4, h->t_dxn, D, st)) return 1;      // d LN3 out = d_hid W_up
     if (launch_layernorm_bwd(h->t_dxn, t.xs2, ly.ln3w, h->t_dx, G(h, b + "norm3.weight"), G(h, b + "norm3.bias"), T, D, st)) return 1;
     // ================= cross-attention: x2 = x1 + CA(LN2 x1, y) =================
-    if (launch_layernorm_bf16(t.xs1, ly.ln2w, ly.ln2b, h->xn, T, D, st)) return 1;
-    if (launch_gemm(EPI_BF16, h->xn, D, ly.wq, D, T, D, D, h->t_q, D, nullptr, nullptr, st)) return 1;               // recompute q
+    if (launch_gemm(EPI_BF16, t.xn1, D, ly.wq, D, T, D, D, h->t_q, D, nullptr, nullptr, st)) return 1;               // recompute q
     if (launch_xattn_bwd(h->t_q, h->t_dx, h->kv + (size_t)l * 2 * D, h->kv + (size_t)B * kvs + (size_t)l * 2 * D, kvs, h->t_a,
                          h->t_dkv + (size_t)l * 2 * D, h->t_dkv + (size_t)B * kvs + (size_t)l * 2 * D, kvs, B, N, D, st))
       return 1;
-    if (launch_gemm_mn(EPI_F32, h->t_a, D, h->xn, D, D, D, T, G(h, b + "cross_attention.q_linear.weight"), D, st)) return 1;  // dq^T xn
+    if (launch_gemm_mn(EPI_F32, h->t_a, D, t.xn1, D, D, D, T, G(h, b + "cross_attention.q_linear.weight"), D, st)) return 1;  // dq^T LN2(x1)
     if (launch_gemm_nn(EPI_F32, h->t_a, D, ly.wq, D, T, D, D, h->t_dxn, D, st)) return 1;           // d LN2 out = dq W_q
     if (launch_layernorm_bwd(h->t_dxn, t.xs1, ly.ln2w, h->t_dx, G(h, b + "norm2.weight"), G(h, b + "norm2.bias"), T, D, st)) return 1;
     // ================= self-attention: x1 = x0 + Attn(qkv(LN1 x0)) =================
     if (launch_self_attention_bwd(t.qkv, h->t_dx, t.xs0, t.xs1, h->t_big, B, N, D, st)) return 1;   // dqkv [T,3D]
-    if (launch_layernorm_bf16(t.xs0, ly.ln1w, ly.ln1b, h->xn, T, D, st)) return 1;
-    if (launch_gemm_mn(EPI_F32, h->t_big, 3 * D, h->xn, D, 3 * D, D, T, G(h, b + "self_attention.qkv_linear.weight"), D, st))
+    if (launch_gemm_mn(EPI_F32, h->t_big, 3 * D, t.xn0, D, 3 * D, D, T, G(h, b + "self_attention.qkv_linear.weight"), D, st))
       return 1;                                                                                     // dqkv^T xn
     if (launch_gemm_nn(EPI_F32, h->t_big, 3 * D, ly.wqkv, D, T, D, 3 * D, h->t_dxn, D, st)) return 1;   // d LN1 out = dqkv W_qkv
     if (launch_layernorm_bwd(h->t_dxn, t.xs0, ly.ln1w, h->t_dx, G(h, b + "norm1.weight"), G(h, b + "norm1.bias"), T, D, st)) return 1;
