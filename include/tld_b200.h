@@ -179,6 +179,21 @@ TLD_API int tld_latent_dequantize(const uint8_t* q, uint16_t* out_fp16, long lon
 TLD_API int tld_image_grid_u8(const void* img, int is_bf16, uint8_t* out, int batch, int h, int w, int ncol, int pad,
                               void* stream);
 
+/* ---- CLIP text tower (tld/diffusion.py:136-140,160,177: clip_model.encode_text(clip.tokenize(prompt)); openai/CLIP model.py) ----
+ * The linear layers run on tld_op_gemm (bias / bias + residual epilogues) and the LayerNorms on tld_op_layernorm; these are the
+ * remaining row-wise pieces.  ids / eot: int64 device arrays ([batch, n_ctx] token ids; [batch] index of the EOT token).
+ *   tld_clip_embed            x[b,t,:] = token_embedding[ids[b,t]] + positional_embedding[t]   (fp32 [batch*n_ctx, D])
+ *   tld_clip_causal_attention out = softmax(q k^T / 8 + causal mask) v per (prompt, head) from qkv bf16 [batch*n_ctx, 3D]
+ *                             (q | k | v as nn.MultiheadAttention's in_proj lays them out), head_dim 64, n_ctx <= 128
+ *   tld_clip_quick_gelu       out = in * sigmoid(1.702 in), bf16, n elements (even)
+ *   tld_clip_final            out[b] = LayerNorm(x[b, eot[b]]) @ proj   (proj fp32 [D, P] row-major = CLIP's text_projection) */
+TLD_API int tld_clip_embed(const int64_t* ids, const float* token_embedding, const float* positional_embedding, float* x,
+                           int batch, int n_ctx, int D, int vocab, void* stream);
+TLD_API int tld_clip_causal_attention(const uint16_t* qkv, uint16_t* out, int batch, int n_ctx, int D, void* stream);
+TLD_API int tld_clip_quick_gelu(const uint16_t* in, uint16_t* out, long long n, void* stream);
+TLD_API int tld_clip_final(const float* x, const int64_t* eot, const float* gamma, const float* beta, const float* proj, float* out,
+                           int batch, int n_ctx, int D, int P, void* stream);
+
 /* ---- training step (tld/train.py:160-170: pred = model(x_noisy, sigma, label); loss.backward()) ---------------
  * tld_train_forward == tld_denoiser_forward but keeps the activations; tld_train_backward turns d(loss)/d(pred) into
  * the fp32 gradient of every parameter, read back per reference state_dict key with tld_train_get_grad (the caller

@@ -98,8 +98,9 @@ def test_configs_match_reference_fields():
     cfg = Cc.LTDConfig(denoiser_cfg=Cc.DenoiserConfig(embed_dim=256))
     back = Cc.from_json(Cc.LTDConfig, Cc.to_json(cfg))
     assert back == cfg
+    Cc.DenoiserConfig(embed_dim=64).check_b200_support()      # any multiple of 64 (heads = embed_dim // 64)
     with pytest.raises(ValueError):
-        Cc.DenoiserConfig(embed_dim=64).check_b200_support()
+        Cc.DenoiserConfig(embed_dim=96).check_b200_support()
 
 
 def test_schedule_matches_oracle():
