@@ -50,7 +50,9 @@ TLD_API const char* tld_last_error(void);
 TLD_API int tld_version(void);
 /* Process-wide tuning switches (tests / experiments): "gemm_ctas" = 0 auto | 1 single-CTA tiles | 2 CTA-pair
  * (cta_group::2) tiles;  "attention_impl" = 0 auto | 1 mma.sync kernel | 3 tcgen05 persistent;
- * "attention_exp_emu" = 0|4|6|8|10 of every 16 exp2 pairs of kernel 3 evaluated on the FMA pipe instead of MUFU;  "fused_mlp" = 1 (default) up-projection + depthwise conv + GELU as one
+ * "attention_exp_emu" = 0|4|6|8|10 of every 16 exp2 pairs of kernel 3 evaluated on the FMA pipe instead of MUFU;  "attention_bwd_impl" = 0 | 1 mma.sync backward kernels (default, faster) | 2 tcgen05 backward kernel when tokens per
+ * sample % 256 == 0;
+ * "fused_mlp" = 1 (default) up-projection + depthwise conv + GELU as one
  * kernel for 16x16 token grids | 0 three separate kernels;  "ln_fold" = 1 norm1 / norm3 folded into the neighbouring GEMMs (their
  * statistics ride on the residual epilogues; measured slower on B200, see csrc/api.cu) | 0 (default) separate LayerNorm kernels;  "pdl" = 1 launch
  * the step kernels with programmatic dependent launch (prologues overlap the previous kernel's tail) | 0 plain launches (default: measured no gain). */

@@ -99,8 +99,18 @@ def test_cross_attention_backward(lib, B, n_tok, D):
 
 
 @pytest.mark.parametrize("B,n_tok,D", [(1, 64, 128), (2, 256, 128), (2, 256, 768), (3, 128, 256),
-                                       (2, 512, 128), (1, 1024, 192), (1, 4096, 64)])   # > 256 tokens: the key-tiled kernels
-def test_self_attention_backward(lib, B, n_tok, D):
+                                       (2, 512, 128), (1, 1024, 192), (1, 4096, 64),    # > 256 tokens: the key-tiled kernels
+                                       (40, 256, 768)])                                 # several CTAs per SM in sequence
+@pytest.mark.parametrize("impl", [1, 2])      # 1: mma.sync kernels (default), 2: tcgen05 kernel where it applies (tokens % 256 == 0)
+def test_self_attention_backward(lib, B, n_tok, D, impl):
+    lib.check(lib.load().tld_set_option(b"attention_bwd_impl", impl), "opt")
+    try:
+        _self_attention_backward(lib, B, n_tok, D)
+    finally:
+        lib.check(lib.load().tld_set_option(b"attention_bwd_impl", 0), "opt")
+
+
+def _self_attention_backward(lib, B, n_tok, D):
     g = torch.Generator(device="cuda").manual_seed(n_tok * 3 + D)
     T, H = B * n_tok, D // 64
     qkv = torch.randn(T, 3 * D, device="cuda", generator=g).bfloat16()

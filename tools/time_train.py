@@ -9,6 +9,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce after the backward instead of overlapped with it")
+    ap.add_argument("--attn-bwd-impl", type=int, default=0)
     ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam(fused=True) + update_ema instead of FusedAdamEMA")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -18,6 +19,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from transformer_latent_diffusion_b200.denoiser import Denoiser
     from transformer_latent_diffusion_b200.train import train_step, update_ema, noise_batch
+    from transformer_latent_diffusion_b200 import _lib
+    _lib.check(_lib.load().tld_set_option(b"attention_bwd_impl", a.attn_bwd_impl), "opt")
     torch.manual_seed(0)
     m = Denoiser(32, 256, 2, 768, 0, 12).cuda().train()
     m.overlap_grad_allreduce = not a.no_overlap

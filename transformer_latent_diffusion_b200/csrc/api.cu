@@ -387,6 +387,11 @@ int tld_set_option(const char* key, int value) {
     g_attention_impl = value;
     return 0;
   }
+  if (k == "attention_bwd_impl") {
+    TLD_CHECK(value >= 0 && value <= 2, "attention_bwd_impl must be 0 / 1 (mma.sync kernels, default) or 2 (tcgen05 kernel when tokens % 256 == 0)");
+    set_attention_bwd_impl(value);
+    return 0;
+  }
   if (k == "fused_mlp") {
     g_fused_mlp = value != 0;
     return 0;

@@ -566,14 +566,27 @@ __global__ void __launch_bounds__(256) attention_bwd_dq_cast_kernel(const float*
   *reinterpret_cast<uint2*>(dqkv + r * 3LL * D + c) = o;
 }
 
+// 0 / 1: the mma.sync kernels (default); 2: the tcgen05 kernel of attention_bwd_tc.cu when n_tok % 256 == 0.  Measured on B200
+// (tools/sab_probe.py, one call = all kernels of the backward of one layer's attention): 256 tokens x batch 32: 128 us (mma.sync)
+// vs 205 us (tcgen05 133 + statistics 52 + cast 8 + memset); 1024 tokens x 8: 441 vs 602 us; 4096 x 2: 1517 vs 2186 us.  The
+// tensor-core version is a serial chain per CTA (TMA -> MMA -> tcgen05.ld -> softmax -> st.shared -> MMA -> atomics) with one CTA
+// per SM (448 TMEM columns), whereas the mma.sync kernel keeps every intermediate in registers and overlaps 8 warps; it needs two
+// query tiles in flight per CTA to win, which 512 TMEM columns do not allow with this tiling.  Kept selectable and parity-tested.
+static int g_attn_bwd_impl = 0;
+void set_attention_bwd_impl(int v) { g_attn_bwd_impl = v; }
+int launch_self_attention_bwd_tc(const bf16* qkv, const float* d_out, const float* lse_g, const float* delta_g, float* dq_acc,
+                                 bf16* dqkv, int B, int n_tok, int D, cudaStream_t st);
+
 int launch_self_attention_bwd(const bf16* qkv, const float* d_out, const float* x_before, const float* x_after, bf16* dqkv,
                               int B, int n_tok, int D, cudaStream_t st) {
   TLD_CHECK(D % 64 == 0 && n_tok % 64 == 0 && (n_tok <= AB_MAXN || n_tok % AB_MAXN == 0),
             "self_attention_bwd: needs embed_dim % 64 == 0 and tokens per sample in {64,128,192,256} or a multiple of 256");
   TLD_CHECK(B <= 65535, "self_attention_bwd: batch too large");
   constexpr int smem = (4 * AB_MAXN * AB_HD + AB_MAXN * 32) * 2 + 2 * AB_MAXN * 4;
-  if (n_tok > AB_MAXN) {
-    // key-tiled path: statistics pass, one CTA per 256-key block accumulating dQ into an fp32 buffer, cast
+  const bool use_tc = g_attn_bwd_impl == 2 && n_tok % AB_MAXN == 0;
+  if (n_tok > AB_MAXN || use_tc) {
+    // key-tiled paths: statistics pass, then either the tcgen05 kernel (one CTA per 128-key block) or the mma.sync kernel (one CTA
+    // per 256-key block), both accumulating dQ into an fp32 buffer; then the cast
     const long long T = (long long)B * n_tok;
     const int H = D / 64, nblk = n_tok / AB_MAXN;
     TLD_CHECK(nblk <= 65535, "self_attention_bwd: too many tokens per sample");
@@ -590,8 +603,12 @@ int launch_self_attention_bwd(const bf16* qkv, const float* d_out, const float* 
     attention_bwd_stats_kernel<<<dim3(H, B, nblk), AB_THREADS, 2 * AB_MAXN * AB_HD * 2, st>>>(qkv, d_out, x_before, x_after, lse_g,
                                                                                             delta_g, n_tok, D);
     TLD_CUDA_OK(cudaGetLastError());
-    attention_bwd_tiled_kernel<<<dim3(H, B, nblk), AB_THREADS, smem, st>>>(qkv, d_out, lse_g, delta_g, dq_acc, dqkv, n_tok, D);
-    TLD_CUDA_OK(cudaGetLastError());
+    if (use_tc) {
+      if (launch_self_attention_bwd_tc(qkv, d_out, lse_g, delta_g, dq_acc, dqkv, B, n_tok, D, st)) return 1;
+    } else {
+      attention_bwd_tiled_kernel<<<dim3(H, B, nblk), AB_THREADS, smem, st>>>(qkv, d_out, lse_g, delta_g, dq_acc, dqkv, n_tok, D);
+      TLD_CUDA_OK(cudaGetLastError());
+    }
     attention_bwd_dq_cast_kernel<<<(unsigned)((T * (D / 4) + 255) / 256), 256, 0, st>>>(dq_acc, dqkv, T, D);
     TLD_CUDA_OK(cudaGetLastError());
     return 0;
