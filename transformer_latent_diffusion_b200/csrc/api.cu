@@ -24,6 +24,7 @@ int fail(const std::string& msg) {
 }
 const char* last_error() { return g_err.c_str(); }
 
+bool ln_fold_requested();   // tld_set_option("ln_fold", 1) is in effect (defined with the option below)
 static int g_pdl = 0;  // measured on B200: no gain (the step is power-capped, not launch-gap bound); kept as an option
 void set_pdl(int v) { g_pdl = v; }
 // Bumped by every tld_set_option call: a captured sampler graph bakes in the kernel selection (attention implementation,
@@ -271,6 +272,7 @@ static int g_fused_mlp = 1;       // tld_set_option("fused_mlp", ...): up-projec
 // ahead, and the 6-stage operand pipeline leaves no room for that.  Kept selectable and parity-tested.
 static int g_ln_fold = 0;
 
+bool ln_fold_requested() { return g_ln_fold != 0; }
 static bool use_ln_fold(const tld_denoiser* h) { return g_ln_fold && h->D % 128 == 0; }
 
 // W' = bf16(gamma (.) W), s, c of every layer from the fp32 shadows, once after each parameter refresh
@@ -535,7 +537,8 @@ int tld_denoiser_set_params_async(tld_denoiser* h, int n, const char* const* key
     e.pad = 0;
     s.filled = true;
     if (filled == REFRESH_BATCH && flush()) return 1;
-    if (s.shadow) {   // the fp32 copy the LayerNorm-folded weights are rebuilt from
+    if (s.shadow && ln_fold_requested()) {   // the fp32 copy the LayerNorm-folded weights are rebuilt from (226 MB per refresh
+                                             // at the 100M model: only written while the fold is switched on)
       RefreshEntry& e2 = batch.e[filled++];
       e2 = e;
       e2.dst = s.shadow;
