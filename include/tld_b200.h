@@ -136,6 +136,10 @@ TLD_API int tld_op_layernorm(const float* x, const float* gamma, const float* be
 /* x[T,D] += softmax(q k^T/8) v per (sample, head) from qkv[T,3D]; impl 0 = auto, 1 = mma.sync kernel,
  * 3 = tcgen05 persistent pipelined kernel (needs n_tok % 128 == 0; auto picks it when that holds) */
 TLD_API int tld_op_self_attention(const uint16_t* qkv, float* x, int batch, int n_tok, int D, int impl, void* stream);
+/* SelfAttention of a block in ONE kernel for 256-token samples (transformer_blocks.py:51-59,24-48,136): x[batch*256, D] +=
+ * softmax(q k^T / 8) v per (sample, head) with [q|k|v] = xn[batch*256, D] Wqkv[3D, D]^T computed inside the kernel by the CTA
+ * pair that owns the (sample, head): the qkv tensor is never written.  Needs n_tok == 256 and D % 64 == 0. */
+TLD_API int tld_op_qkv_attention(const uint16_t* xn, const uint16_t* Wqkv, float* x, int batch, int n_tok, int D, void* stream);
 /* MLPSepConv front half in one kernel for 16x16-token samples (transformer_blocks.py:95-103): out[batch*256, N] bf16 =
  * GELU(dwconv3x3(A[batch*256, K] W[N, K]^T + col_c) + dw_b) with the hidden tensor kept on chip (CTA-pair tile = one image,
  * halo row exchanged through distributed shared memory).  Optional LayerNorm fold: row_sums [batch*256, 2] = (sum, sum of

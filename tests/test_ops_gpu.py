@@ -181,6 +181,28 @@ def test_self_attention(lib, B, n_tok, D, impl):
     assert rel_fro(x - (ref - o), o) < 6e-3, _err_map(x, ref)
 
 
+@pytest.mark.parametrize("B,D", [(1, 64), (2, 128), (3, 768), (5, 192), (40, 768), (75, 320), (128, 768)])
+def test_qkv_attention_fused(lib, B, D):
+    """qkv projection + attention + residual add in one CTA-pair kernel (256 tokens per sample) vs fp32 math on bf16-rounded q, k, v"""
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + D)
+    n_tok, T, H = 256, B * 256, D // 64
+    xn = torch.randn(T, D, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(3 * D, D, device="cuda", generator=g) * (1.5 / D ** 0.5)).bfloat16()
+    x = torch.randn(T, D, device="cuda", generator=g)
+    qkv = (xn.float() @ w.float().t()).bfloat16()
+    q, k, v = (t.float().view(B, n_tok, H, 64).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=1))
+    o = (torch.softmax((q @ k.transpose(-1, -2)) / 8.0, -1) @ v).permute(0, 2, 1, 3).reshape(T, D)
+    x0 = x.clone()
+    lib.check(lib.load().tld_op_qkv_attention(lib.ptr(xn), lib.ptr(w), lib.ptr(x), B, n_tok, D, _stream()), "qkv_attention")
+    torch.cuda.synchronize()
+    assert torch.isfinite(x).all()
+    assert rel_fro(x - x0, o) < 6e-3, _err_map(x, x0 + o)
+    # and against the two-kernel path (GEMM -> qkv in HBM -> attention_tc2) on the same operands
+    x2 = x0.clone()
+    lib.check(lib.load().tld_op_self_attention(lib.ptr(qkv), lib.ptr(x2), B, n_tok, D, 3, _stream()), "attn")
+    assert rel_fro(x - x0, x2 - x0) < 6e-3
+
+
 @pytest.mark.parametrize("emu", [0, 4, 6, 8, 10])
 @pytest.mark.parametrize("qk_scale", [1.0, 4.0])
 def test_self_attention_persistent_variants(lib, emu, qk_scale):

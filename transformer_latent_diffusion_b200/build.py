@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libtld_b200.so")
-SOURCES = ["api.cu", "gemm.cu", "rowwise.cu", "attention.cu", "attention_tc2.cu", "vae_kernels.cu", "backward.cu", "attention_bwd.cu", "train.cu", "optim.cu", "gemm_dwconv.cu", "clip_kernels.cu", "attention_bwd_tc.cu"]
+SOURCES = ["api.cu", "gemm.cu", "rowwise.cu", "attention.cu", "attention_tc2.cu", "vae_kernels.cu", "backward.cu", "attention_bwd.cu", "train.cu", "optim.cu", "gemm_dwconv.cu", "clip_kernels.cu", "attention_bwd_tc.cu", "qkv_attention.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -48,7 +48,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         s = os.path.join(CSRC, src)
         o = os.path.join(BUILD, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + headers):
-            jobs.append([nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-c", s, "-o", o])
+            jobs.append([nvcc, *NVCC_FLAGS, *os.environ.get("TLD_NVCC_EXTRA", "").split(),   # developer builds, e.g. -DTLD_TRACE
+                         *(["-Xptxas", "-v"] if verbose else []), "-c", s, "-o", o])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)

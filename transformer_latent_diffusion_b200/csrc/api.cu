@@ -291,6 +291,8 @@ static int ensure_fold(tld_denoiser* h, cudaStream_t st) {
 
 // the fused MLP front half needs one CTA-pair tile per sample (16x16 token grid) and whole 256-channel tiles
 static bool use_fused_mlp(const tld_denoiser* h) { return g_fused_mlp && h->G == 16 && h->H4 % 256 == 0; }
+static int g_fused_qkv = 1;       // tld_set_option("fused_qkv", ...): qkv projection + attention in one kernel (256 tokens)
+static bool use_fused_qkv(const tld_denoiser* h) { return g_fused_qkv && h->N == 256 && !use_ln_fold(h); }
 
 // The L decoder blocks + output projection on the tokens already in h->x_res (transformer_blocks.py:135-139).
 static int run_blocks(tld_denoiser* h, int batch, const float* kv0, long long kv0_stride, const float* kv1,
@@ -310,9 +312,11 @@ static int run_blocks(tld_denoiser* h, int batch, const float* kv0, long long kv
       if (launch_gemm(EPI_LNFOLD_BF16, h->xb[cur], D, fl.wqkv_f, D, T, 3 * D, D, h->qkv, 3 * D, fl.c_qkv, nullptr, st, &ln)) return 1;
     } else {
       if (launch_layernorm_bf16(h->x_res, ly.ln1w, ly.ln1b, h->xn, T, D, st)) return 1;
-      if (launch_gemm(EPI_BF16, h->xn, D, ly.wqkv, D, T, 3 * D, D, h->qkv, 3 * D, nullptr, nullptr, st)) return 1;
+      if (!use_fused_qkv(h) && launch_gemm(EPI_BF16, h->xn, D, ly.wqkv, D, T, 3 * D, D, h->qkv, 3 * D, nullptr, nullptr, st)) return 1;
     }
-    if (launch_self_attention(h->qkv, h->x_res, batch, N, D, st, g_attention_impl)) return 1;
+    if (use_fused_qkv(h)) {   // the CTA pair that owns a (sample, head) projects q, k, v itself: qkv never touches HBM
+      if (launch_qkv_attention(h->xn, ly.wqkv, h->x_res, batch, N, D, st)) return 1;
+    } else if (launch_self_attention(h->qkv, h->x_res, batch, N, D, st, g_attention_impl)) return 1;
     // x = CrossAttention(LN2(x), y) + x
     if (launch_layernorm_bf16(h->x_res, ly.ln2w, ly.ln2b, h->xn, T, D, st)) return 1;
     XattnArgs xa;
@@ -359,7 +363,7 @@ static int run_blocks(tld_denoiser* h, int batch, const float* kv0, long long kv
 }
 
 static int kernels_per_forward(const tld_denoiser* h) {
-  const int per_layer = 9 - (use_fused_mlp(h) ? 1 : 0) - (use_ln_fold(h) ? 2 : 0);
+  const int per_layer = 9 - (use_fused_mlp(h) ? 1 : 0) - (use_ln_fold(h) ? 2 : 0) - (use_fused_qkv(h) ? 1 : 0);
   return 1 + (use_ln_fold(h) ? 1 : 0) + per_layer * h->L + 1;
 }
 
@@ -392,6 +396,10 @@ int tld_set_option(const char* key, int value) {
   if (k == "attention_bwd_impl") {
     TLD_CHECK(value >= 0 && value <= 2, "attention_bwd_impl must be 0 / 1 (mma.sync kernels, default) or 2 (tcgen05 kernel when tokens % 256 == 0)");
     set_attention_bwd_impl(value);
+    return 0;
+  }
+  if (k == "fused_qkv") {
+    g_fused_qkv = value != 0;
     return 0;
   }
   if (k == "fused_mlp") {
@@ -812,6 +820,11 @@ int tld_op_self_attention(const uint16_t* qkv, float* x, int batch, int n_tok, i
             "tld_op_self_attention: impl must be 0 (auto), 1 (mma.sync) or 3 (tcgen05 persistent)");
   return launch_self_attention(reinterpret_cast<const bf16*>(qkv), x, batch, n_tok, D,
                                reinterpret_cast<cudaStream_t>(stream), impl);
+}
+
+int tld_op_qkv_attention(const uint16_t* xn, const uint16_t* Wqkv, float* x, int batch, int n_tok, int D, void* stream) {
+  return launch_qkv_attention(reinterpret_cast<const bf16*>(xn), reinterpret_cast<const bf16*>(Wqkv), x, batch, n_tok, D,
+                              reinterpret_cast<cudaStream_t>(stream));
 }
 
 int tld_op_gemm_up_dwconv_gelu(const uint16_t* A, const uint16_t* W, const float* col_c, const float* col_s,

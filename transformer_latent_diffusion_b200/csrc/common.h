@@ -159,6 +159,9 @@ int make_tmap_tokens3d(CUtensorMap* m, const void* base, int B, int npos, int C,
 int launch_self_attention(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st, int impl = 0);
 int launch_self_attention_mma(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st);
 int launch_self_attention_tc2(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st);
+// qkv projection + attention + residual add in one CTA-pair kernel (256 tokens per sample): qkv_attention.cu
+int launch_qkv_attention(const bf16* xn, const bf16* wqkv, float* x, int B, int n_tok, int D, cudaStream_t st);
+void set_qkv_attention_exp_emu(int v);
 void set_attention_exp_emu(int pairs_of_16);
 void set_attention_bwd_impl(int v);   // 0 / 1 mma.sync kernels (default), 2 tcgen05 kernel when tokens % 256 == 0  // attention_tc2: share of exp2 evaluated on the FMA pipe instead of MUFU
 
