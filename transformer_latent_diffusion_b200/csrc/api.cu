@@ -398,6 +398,11 @@ int tld_set_option(const char* key, int value) {
     set_attention_bwd_impl(value);
     return 0;
   }
+  if (k == "qkv_exp_emu") {
+    TLD_CHECK(value == 0 || value == 4 || value == 6 || value == 8, "qkv_exp_emu (exp2 pairs per 16 on the FMA pipe, fused qkv + attention kernel) must be 0, 4, 6 or 8");
+    set_qkv_attention_exp_emu(value);
+    return 0;
+  }
   if (k == "fused_qkv") {
     g_fused_qkv = value != 0;
     return 0;
