@@ -405,12 +405,17 @@ def run_b200(args) -> None:
                    "images_per_gpu_per_step": B, "n_iter": N_ITER, "class_guidance": GUIDANCE, "cfg_batch": 2 * B,
                    "parallelism": f"batch-sharded x{world}, no collective", "weights": "random-init",
                    "l2": "inputs larger than L2: 202 MB bf16 weights + >1 GB activations per step vs 126 MB L2",
-                   "denoiser": "libtld_b200 (hand-written sm_100a, CUDA-graph step: LayerNorm folded into the GEMMs, fused "
-                               "up-projection + depthwise conv + GELU)",
+                   "denoiser": "libtld_b200 (hand-written sm_100a, CUDA-graph step, 5 kernels per block: norm1, fused qkv projection + "
+                               "attention, norm2 + folded 2-token cross-attention + norm3, fused up-projection + depthwise conv + "
+                               "GELU, down-projection + residual)",
                    "vae_decode": "libtld_b200 tcgen05 implicit-GEMM conv3x3 + fused GroupNorm/SiLU/upsample kernels (bf16); parity "
                                  "UNPINNED (third-party diffusers absent: checked against oracle/vae_oracle.py only)"},
         "denoiser_step_ms": loop_ms / N_ITER, "denoiser_only_images_per_s_per_gpu": B / (loop_ms * 1e-3),
         "denoiser_step_frac_of_sustained_bf16_peak": step_flops / (loop_ms / N_ITER * 1e-3) / 1e12 / sustained,
+        "flops_accounting": "SURVEY.md 8d model FLOPs of the reference's formulation (24 n d^2 + ... per block); the folded "
+                            "cross-attention does not execute the 2 n d^2 q-projection of each block, so executed_step_tflop is lower",
+        "model_step_tflop": step_flops / 1e12,
+        "executed_step_tflop": (step_flops - 2 * B * L * 2 * (IMG // 2) ** 2 * D * D) / 1e12,
         "flops_per_image": flops_img,
         "model_tflops_whole_step": flops_img * value / 1e12,
         "frac_of_sustained_bf16_peak_whole_step": flops_img * value / 1e12 / (sustained * world),

@@ -136,6 +136,13 @@ TLD_API int tld_op_layernorm(const float* x, const float* gamma, const float* be
 /* x[T,D] += softmax(q k^T/8) v per (sample, head) from qkv[T,3D]; impl 0 = auto, 1 = mma.sync kernel,
  * 3 = tcgen05 persistent pipelined kernel (needs n_tok % 128 == 0; auto picks it when that holds) */
 TLD_API int tld_op_self_attention(const uint16_t* qkv, float* x, int batch, int n_tok, int D, int impl, void* stream);
+/* norm2 + CrossAttention over the two conditioning tokens + residual + norm3 in ONE row-wise kernel (transformer_blocks.py:
+ * 62-75,137,138): x[batch*n_tok, D] += softmax2(q k0, q k1) (v0, v1) with q = LN2(x) Wq^T folded into the keys (u = Wq_h^T k_h
+ * per head, so q is never formed), y = bf16(LN3(x_new)).  kv0 / kv1 [batch, 2D] (K | V rows of the noise and label tokens),
+ * uk_scratch [2 * batch, D / 64, D] fp32.  Needs D % 128 == 0 (<= 1024) and n_tok % 32 == 0. */
+TLD_API int tld_op_ln_xattn_ln(float* x, const float* g2, const float* b2, const float* g3, const float* b3, const uint16_t* Wq,
+                               const float* kv0, const float* kv1, int batch, int n_tok, int D, float* uk_scratch, uint16_t* y,
+                               void* stream);
 /* SelfAttention of a block in ONE kernel for 256-token samples (transformer_blocks.py:51-59,24-48,136): x[batch*256, D] +=
  * softmax(q k^T / 8) v per (sample, head) with [q|k|v] = xn[batch*256, D] Wqkv[3D, D]^T computed inside the kernel by the CTA
  * pair that owns the (sample, head): the qkv tensor is never written.  Needs n_tok == 256 and D % 64 == 0. */

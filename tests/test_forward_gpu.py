@@ -153,9 +153,9 @@ def test_sampler_repeatable_and_stats():
             ref = O.generate_latents(sd, cfg, labels, seeds, n_iter=n_iter, exponent=exponent)
         assert rel_fro(a, ref) < 3 * TOL, (n_iter, exponent, rel_fro(a, ref))
     ms, launches = gen.last_stats()
-    # per step: embed + 9 kernels per block (8x8 token grid: no fused MLP) + out-projection + CFG update + step counter;
-    # 3 prologue launches
-    assert ms > 0 and launches == 50 * (9 * 1 + 4) + 3
+    # per step: embed + 7 kernels per block (8x8 token grid: no fused MLP / fused self-attention; norm2 + cross-attention + norm3
+    # are one row-wise kernel) + out-projection + CFG update + step counter; 3 prologue launches + the key fold of the layer
+    assert ms > 0 and launches == 50 * (7 * 1 + 4) + 3 + 1
 
 
 def test_in_place_weight_updates_are_always_seen():
@@ -340,3 +340,34 @@ def test_forward_with_layernorm_fold_option(img, D, L, B):
         _lib.check(_lib.load().tld_set_option(b"ln_fold", 0), "opt")
     assert torch.equal(out, out2)          # partial statistics are summed in a fixed order: deterministic
     assert rel_fro(out, ref) < TOL, f"rel_fro={rel_fro(out, ref):.3e}"
+
+
+@pytest.mark.parametrize("img,D,L,B", [(32, 768, 2, 3), (32, 256, 3, 5), (16, 384, 2, 2), (64, 128, 1, 1)])
+def test_forward_with_fused_attention_kernels_on_and_off(img, D, L, B):
+    """fused_qkv (qkv projection + attention in one CTA-pair kernel, 256 tokens) and fused_xattn (norm2 + cross-attention +
+    norm3 as one row-wise kernel on keys folded through Wq): both paths against the oracle, and against each other."""
+    from transformer_latent_diffusion_b200 import _lib
+
+    cfg = O.OracleCfg(image_size=img, embed_dim=D, n_layers=L)
+    sd = O.synth_state_dict(cfg, 191)
+    g = torch.Generator().manual_seed(192)
+    sd = {k: (v + 0.1 * torch.randn(v.shape, generator=g) if ".norm" in k else v) for k, v in sd.items()}   # non-trivial gamma / beta
+    x = torch.randn(B, 4, img, img, generator=g)
+    t = torch.rand(B, 1, generator=g)
+    lab = torch.randn(B, 768, generator=g)
+    with torch.no_grad():
+        ref = O.denoiser_forward(sd, cfg, x, t, lab)
+    m = _model(cfg, sd)
+    outs = {}
+    try:
+        for qkv, xattn in [(1, 1), (0, 1), (1, 0), (0, 0)]:
+            _lib.check(_lib.load().tld_set_option(b"fused_qkv", qkv), "opt")
+            _lib.check(_lib.load().tld_set_option(b"fused_xattn", xattn), "opt")
+            with torch.no_grad():
+                outs[(qkv, xattn)] = m(x.cuda(), t.cuda(), lab.cuda()).clone()
+    finally:
+        _lib.check(_lib.load().tld_set_option(b"fused_qkv", 1), "opt")
+        _lib.check(_lib.load().tld_set_option(b"fused_xattn", 1), "opt")
+    for key, out in outs.items():
+        assert rel_fro(out, ref) < TOL, f"{key}: rel_fro={rel_fro(out, ref):.3e}"
+    assert rel_fro(outs[(1, 1)], outs[(0, 0)]) < TOL

@@ -181,6 +181,35 @@ def test_self_attention(lib, B, n_tok, D, impl):
     assert rel_fro(x - (ref - o), o) < 6e-3, _err_map(x, ref)
 
 
+@pytest.mark.parametrize("B,n_tok,D", [(2, 64, 128), (3, 256, 768), (5, 32, 256), (37, 256, 768), (2, 1024, 384), (4, 96, 1024)])
+def test_ln_xattn_ln_fused(lib, B, n_tok, D):
+    """norm2 + 2-token cross-attention (q folded into the keys) + residual + norm3 in one row-wise kernel vs fp32 torch"""
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + D)
+    T, H = B * n_tok, D // 64
+    x = torch.randn(T, D, device="cuda", generator=g) * 2 + 0.3
+    g2, b2, g3, b3 = (torch.randn(D, device="cuda", generator=g) * s + o for s, o in ((0.2, 1.0), (0.2, 0.0), (0.2, 1.0), (0.2, 0.0)))
+    wq = (torch.randn(D, D, device="cuda", generator=g) / D ** 0.5).bfloat16()
+    kv0 = torch.randn(B, 2 * D, device="cuda", generator=g)
+    kv1 = torch.randn(B, 2 * D, device="cuda", generator=g)
+    xn2 = torch.nn.functional.layer_norm(x.double(), (D,), g2.double(), b2.double())
+    q = (xn2 @ wq.double().t()).view(B, n_tok, H, 64)
+    k = torch.stack([kv0[:, :D], kv1[:, :D]], 1).double().view(B, 2, H, 64)
+    v = torch.stack([kv0[:, D:], kv1[:, D:]], 1).double().view(B, 2, H, 64)
+    p = torch.softmax(torch.einsum("bnhd,bjhd->bnhj", q, k) / 8.0, -1)
+    o = torch.einsum("bnhj,bjhd->bnhd", p, v).reshape(T, D)
+    x_ref = x.double() + o
+    y_ref = torch.nn.functional.layer_norm(x_ref, (D,), g3.double(), b3.double())
+    x0 = x.clone()
+    uk = torch.empty(2 * B, H, D, device="cuda")
+    y = torch.empty(T, D, device="cuda", dtype=torch.bfloat16)
+    lib.check(lib.load().tld_op_ln_xattn_ln(lib.ptr(x), lib.ptr(g2), lib.ptr(b2), lib.ptr(g3), lib.ptr(b3), lib.ptr(wq), lib.ptr(kv0),
+                                            lib.ptr(kv1), B, n_tok, D, lib.ptr(uk), lib.ptr(y), _stream()), "ln_xattn_ln")
+    torch.cuda.synchronize()
+    assert torch.isfinite(x).all() and torch.isfinite(y.float()).all()
+    assert rel_fro((x - x0).double(), o) < 2e-5, _err_map(x, x_ref.float())
+    assert rel_fro(y.double(), y_ref) < 4e-3
+
+
 @pytest.mark.parametrize("B,D", [(1, 64), (2, 128), (3, 768), (5, 192), (40, 768), (75, 320), (128, 768)])
 def test_qkv_attention_fused(lib, B, D):
     """qkv projection + attention + residual add in one CTA-pair kernel (256 tokens per sample) vs fp32 math on bf16-rounded q, k, v"""

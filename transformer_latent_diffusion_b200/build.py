@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libtld_b200.so")
-SOURCES = ["api.cu", "gemm.cu", "rowwise.cu", "attention.cu", "attention_tc2.cu", "vae_kernels.cu", "backward.cu", "attention_bwd.cu", "train.cu", "optim.cu", "gemm_dwconv.cu", "clip_kernels.cu", "attention_bwd_tc.cu", "qkv_attention.cu"]
+SOURCES = ["api.cu", "gemm.cu", "rowwise.cu", "attention.cu", "attention_tc2.cu", "vae_kernels.cu", "backward.cu", "attention_bwd.cu", "train.cu", "optim.cu", "gemm_dwconv.cu", "clip_kernels.cu", "attention_bwd_tc.cu", "qkv_attention.cu", "xattn_rowwise.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

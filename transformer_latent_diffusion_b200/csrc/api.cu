@@ -240,6 +240,8 @@ static int ensure_cond(tld_denoiser* h, int rows) {
   TLD_CUDA_OK(cudaDeviceSynchronize());
   if (h->ycond) cudaFree(h->ycond);
   if (h->kv) cudaFree(h->kv);
+  if (h->uk) cudaFree(h->uk);
+  h->uk = nullptr;
   if (h->tlevels) cudaFree(h->tlevels);
   if (h->cond_scratch) cudaFree(h->cond_scratch);
   h->ycond = nullptr; h->kv = nullptr; h->tlevels = nullptr; h->cond_scratch = nullptr;
@@ -251,6 +253,9 @@ static int ensure_cond(tld_denoiser* h, int rows) {
   const int r = ((rows + 127) / 128) * 128;
   if (dev_alloc(h, &h->ycond, (long long)r * h->D, false)) return 1;
   if (dev_alloc(h, &h->kv, (long long)r * h->L * 2 * h->D, false)) return 1;
+  // folded cross-attention keys: (D / 64) D floats per row and layer; past 1 GiB the q-GEMM path is used instead
+  const long long uk_elems = (long long)r * h->L * (h->D / 64) * h->D;
+  if (uk_elems * 4 <= (1ll << 30) && dev_alloc(h, &h->uk, uk_elems, false)) return 1;
   if (dev_alloc(h, &h->tlevels, r, false)) return 1;
   if (dev_alloc(h, &h->cond_scratch, (long long)r * (h->E + 2 * h->D), false)) return 1;
   h->ws_cond_rows = r;
@@ -291,6 +296,20 @@ static int ensure_fold(tld_denoiser* h, cudaStream_t st) {
 
 // the fused MLP front half needs one CTA-pair tile per sample (16x16 token grid) and whole 256-channel tiles
 static bool use_fused_mlp(const tld_denoiser* h) { return g_fused_mlp && h->G == 16 && h->H4 % 256 == 0; }
+static int g_fused_xattn = 1;     // tld_set_option("fused_xattn", ...): norm2 + cross-attention + residual + norm3 in one row-wise kernel
+static bool use_fused_xattn(const tld_denoiser* h) {
+  return g_fused_xattn && h->uk && ln_xattn_ln_supported(h->D, h->N) && !use_ln_fold(h);
+}
+// u = Wq_h^T k_h for every row of the K/V table and every layer (once per forward, once per generation in the sampler)
+static int fold_xattn_keys(tld_denoiser* h, int rows, cudaStream_t st) {
+  if (!use_fused_xattn(h)) return 0;
+  const long long kvs = (long long)h->L * 2 * h->D, uks = (long long)h->L * (h->D / 64) * h->D;
+  for (int l = 0; l < h->L; ++l)
+    if (launch_xattn_fold_keys(h->kv + (size_t)l * 2 * h->D, kvs, rows, h->layers[l].wq, h->uk + (size_t)l * (h->D / 64) * h->D, uks,
+                               h->D, st))
+      return 1;
+  return 0;
+}
 static int g_fused_qkv = 1;       // tld_set_option("fused_qkv", ...): qkv projection + attention in one kernel (256 tokens)
 static bool use_fused_qkv(const tld_denoiser* h) { return g_fused_qkv && h->N == 256 && !use_ln_fold(h); }
 
@@ -318,6 +337,15 @@ static int run_blocks(tld_denoiser* h, int batch, const float* kv0, long long kv
       if (launch_qkv_attention(h->xn, ly.wqkv, h->x_res, batch, N, D, st)) return 1;
     } else if (launch_self_attention(h->qkv, h->x_res, batch, N, D, st, g_attention_impl)) return 1;
     // x = CrossAttention(LN2(x), y) + x
+    if (use_fused_xattn(h)) {   // norm2, the (folded) q projection, the 2-key softmax, the residual and norm3 in one row-wise pass
+      const long long kvs_all = (long long)h->L * 2 * D, uks = (long long)h->L * (D / 64) * D;
+      const float* uk0 = h->uk + ((kv0 - h->kv) / kvs_all) * uks + (size_t)l * (D / 64) * D;
+      const float* uk1 = h->uk + ((kv1 - h->kv) / kvs_all) * uks + (size_t)l * (D / 64) * D;
+      if (launch_ln_xattn_ln(h->x_res, ly.ln2w, ly.ln2b, ly.ln3w, ly.ln3b, uk0, kv0_stride == 0 ? 0 : uks, uk1,
+                             kv1_stride == 0 ? 0 : uks, kv0 + (size_t)l * 2 * D, kv0_stride, kv1 + (size_t)l * 2 * D, kv1_stride,
+                             step_ptr, h->xn, T, N, D, st))
+        return 1;
+    } else {
     if (launch_layernorm_bf16(h->x_res, ly.ln2w, ly.ln2b, h->xn, T, D, st)) return 1;
     XattnArgs xa;
     xa.kv0 = kv0 + (size_t)l * 2 * D;
@@ -334,10 +362,11 @@ static int run_blocks(tld_denoiser* h, int batch, const float* kv0, long long kv
     } else {
       if (launch_gemm(EPI_XATTN_RESID_F32, h->xn, D, ly.wq, D, T, D, D, h->x_res, D, nullptr, &xa, st)) return 1;
     }
+    }
     // x = MLPSepConv(LN3(x)) + x
     const bf16* a_up = h->xn;
     if (fold) a_up = h->xb[cur];
-    else if (launch_layernorm_bf16(h->x_res, ly.ln3w, ly.ln3b, h->xn, T, D, st)) return 1;
+    else if (!use_fused_xattn(h) && launch_layernorm_bf16(h->x_res, ly.ln3w, ly.ln3b, h->xn, T, D, st)) return 1;
     if (use_fused_mlp(h)) {
       if (launch_gemm_up_dwconv_gelu(a_up, D, fold ? fl.wup_f : ly.wup, D, T, H4, D, fold ? fl.c_up : ly.bup, fold ? fl.s_up : nullptr,
                                      fold ? h->part[cur] : nullptr, fold ? n_part : 0, 1e-5f, ly.dww9, ly.dwb, h->hid2, st))
@@ -363,7 +392,8 @@ static int run_blocks(tld_denoiser* h, int batch, const float* kv0, long long kv
 }
 
 static int kernels_per_forward(const tld_denoiser* h) {
-  const int per_layer = 9 - (use_fused_mlp(h) ? 1 : 0) - (use_ln_fold(h) ? 2 : 0) - (use_fused_qkv(h) ? 1 : 0);
+  const int per_layer = 9 - (use_fused_mlp(h) ? 1 : 0) - (use_ln_fold(h) ? 2 : 0) - (use_fused_qkv(h) ? 1 : 0) -
+                        (use_fused_xattn(h) ? 2 : 0);
   return 1 + (use_ln_fold(h) ? 1 : 0) + per_layer * h->L + 1;
 }
 
@@ -401,6 +431,10 @@ int tld_set_option(const char* key, int value) {
   if (k == "qkv_exp_emu") {
     TLD_CHECK(value == 0 || value == 4 || value == 6 || value == 8, "qkv_exp_emu (exp2 pairs per 16 on the FMA pipe, fused qkv + attention kernel) must be 0, 4, 6 or 8");
     set_qkv_attention_exp_emu(value);
+    return 0;
+  }
+  if (k == "fused_xattn") {
+    g_fused_xattn = value != 0;
     return 0;
   }
   if (k == "fused_qkv") {
@@ -472,7 +506,7 @@ void tld_denoiser_destroy(tld_denoiser* h) {
   cudaDeviceSynchronize();
   free_workspace(h);
   for (void* p : h->allocs) cudaFree(p);
-  void* extra[] = {h->ycond, h->kv, h->tlevels, h->cond_scratch, h->x_t, h->x0_prev, h->x0_out, h->step_table};
+  void* extra[] = {h->ycond, h->kv, h->uk, h->tlevels, h->cond_scratch, h->x_t, h->x0_prev, h->x0_out, h->step_table};
   for (void* p : extra)
     if (p) cudaFree(p);
   for (cudaEvent_t e : h->ev_grad)
@@ -590,6 +624,7 @@ int tld_denoiser_forward(tld_denoiser* h, const float* x, const float* noise_lev
   if (launch_gemm(EPI_F32, h->ycond, h->D, h->wkv_all, h->D, 2 * batch, int(kvs), h->D, h->kv, int(kvs), nullptr,
                   nullptr, st))
     return 1;
+  if (fold_xattn_keys(h, 2 * batch, st)) return 1;
   if (launch_embed(x, batch, batch, h->C, h->img, h->patch, h->D, h->emb, h->x_res, st)) return 1;
   if (use_ln_fold(h) && ensure_fold(h, st)) return 1;
   return run_blocks(h, batch, h->kv, kvs, h->kv + (size_t)batch * kvs, kvs, nullptr, out, st);
@@ -704,6 +739,7 @@ int tld_sampler_generate(tld_denoiser* h, const float* labels, const float* seed
   if (launch_gemm(EPI_F32, h->ycond, h->D, h->wkv_all, h->D, calls + Beff, int(kvs), h->D, h->kv, int(kvs), nullptr,
                   nullptr, st))
     return 1;
+  if (fold_xattn_keys(h, calls + Beff, st)) return 1;
   const float* kv1 = h->kv;
   const float* kv0 = h->kv + (size_t)Beff * kvs;
 
@@ -733,7 +769,7 @@ int tld_sampler_generate(tld_denoiser* h, const float* labels, const float* seed
   TLD_CUDA_OK(cudaMemcpyAsync(latent_out, h->x0_out, sizeof(float) * img_elems, cudaMemcpyDeviceToDevice, st));
   TLD_CUDA_OK(cudaEventRecord(h->ev_out, st));
   TLD_CUDA_OK(cudaStreamWaitEvent(caller, h->ev_out, 0));
-  h->last_launches = (long long)calls * (kernels_per_forward(h) + 2) + 3;
+  h->last_launches = (long long)calls * (kernels_per_forward(h) + 2) + 3 + (use_fused_xattn(h) ? h->L : 0);
   h->last_loop_ms = -1.f;
   return 0;
 }
@@ -825,6 +861,17 @@ int tld_op_self_attention(const uint16_t* qkv, float* x, int batch, int n_tok, i
             "tld_op_self_attention: impl must be 0 (auto), 1 (mma.sync) or 3 (tcgen05 persistent)");
   return launch_self_attention(reinterpret_cast<const bf16*>(qkv), x, batch, n_tok, D,
                                reinterpret_cast<cudaStream_t>(stream), impl);
+}
+
+int tld_op_ln_xattn_ln(float* x, const float* g2, const float* b2, const float* g3, const float* b3, const uint16_t* Wq,
+                       const float* kv0, const float* kv1, int batch, int n_tok, int D, float* uk_scratch, uint16_t* y, void* stream) {
+  TLD_CHECK(uk_scratch != nullptr && D % 64 == 0, "tld_op_ln_xattn_ln: needs a [2 * batch, D / 64, D] fp32 scratch buffer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long uks = (long long)(D / 64) * D;
+  if (launch_xattn_fold_keys(kv0, 2LL * D, batch, reinterpret_cast<const bf16*>(Wq), uk_scratch, uks, D, st)) return 1;
+  if (launch_xattn_fold_keys(kv1, 2LL * D, batch, reinterpret_cast<const bf16*>(Wq), uk_scratch + (size_t)batch * uks, uks, D, st)) return 1;
+  return launch_ln_xattn_ln(x, g2, b2, g3, b3, uk_scratch, uks, uk_scratch + (size_t)batch * uks, uks, kv0, 2LL * D, kv1, 2LL * D,
+                            nullptr, reinterpret_cast<bf16*>(y), batch * n_tok, n_tok, D, st);
 }
 
 int tld_op_qkv_attention(const uint16_t* xn, const uint16_t* Wqkv, float* x, int batch, int n_tok, int D, void* stream) {

@@ -159,6 +159,14 @@ int make_tmap_tokens3d(CUtensorMap* m, const void* base, int B, int npos, int C,
 int launch_self_attention(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st, int impl = 0);
 int launch_self_attention_mma(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st);
 int launch_self_attention_tc2(const bf16* qkv, float* x, int B, int n_tok, int D, cudaStream_t st);
+// norm2 + 2-token cross-attention + residual + norm3 as one row-wise kernel on keys folded through Wq: xattn_rowwise.cu
+int launch_xattn_fold_keys(const float* kv, long long kv_stride, int R, const bf16* wq, float* uk, long long uk_stride, int D,
+                           cudaStream_t st);
+bool ln_xattn_ln_supported(int D, int n_tok);
+int launch_ln_xattn_ln(float* x, const float* g2, const float* b2, const float* g3, const float* b3, const float* uk0,
+                       long long uk0_stride, const float* uk1, long long uk1_stride, const float* kv0, long long kv0_stride,
+                       const float* kv1, long long kv1_stride, const int* step_ptr, bf16* y, int rows, int n_tok, int D,
+                       cudaStream_t st);
 // qkv projection + attention + residual add in one CTA-pair kernel (256 tokens per sample): qkv_attention.cu
 int launch_qkv_attention(const bf16* xn, const bf16* wqkv, float* x, int B, int n_tok, int D, cudaStream_t st);
 void set_qkv_attention_exp_emu(int v);

@@ -66,6 +66,7 @@ struct tld_denoiser {
   int ws_cond_rows = 0;
   bf16* ycond = nullptr;    // [rows, D]
   float* kv = nullptr;      // [rows, L*2D]
+  float* uk = nullptr;      // [rows, L, H, D] cross-attention keys folded through Wq (xattn_rowwise.cu); nullptr = table too large
   float* tlevels = nullptr; // [max steps]
   float* cond_scratch = nullptr;  // [rows, E + 2 D] fp32 intermediates of the conditioning MLP (inference path)
 
