@@ -181,7 +181,7 @@ def test_self_attention(lib, B, n_tok, D, impl):
     assert rel_fro(x - (ref - o), o) < 6e-3, _err_map(x, ref)
 
 
-@pytest.mark.parametrize("B,n_tok,D", [(2, 64, 128), (3, 256, 768), (5, 32, 256), (37, 256, 768), (2, 1024, 384), (4, 96, 1024)])
+@pytest.mark.parametrize("B,n_tok,D", [(2, 64, 128), (3, 256, 768), (5, 32, 256), (37, 256, 768), (2, 1024, 384), (4, 96, 1024), (3, 36, 512), (9, 256, 896)])
 def test_ln_xattn_ln_fused(lib, B, n_tok, D):
     """norm2 + 2-token cross-attention (q folded into the keys) + residual + norm3 in one row-wise kernel vs fp32 torch"""
     g = torch.Generator(device="cuda").manual_seed(B * 100 + D)

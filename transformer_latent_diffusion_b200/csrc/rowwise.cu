@@ -209,13 +209,14 @@ __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ x,
   __shared__ float s_t[8][64];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = img / patch, N = g * g, pd = C * patch * patch;
+  // tokens of the Bx distinct images; output image b + k Bx (k < Bout / Bx: the CFG pair embeds the same x_t twice) gets a copy
   const long long tok = (long long)blockIdx.x * 8 + wib;
   pdl_launch_dependents();
-  if (tok >= (long long)Bout * N) return;
+  if (tok >= (long long)Bx * N) return;
   pdl_wait();
   const int b = int(tok / N), n = int(tok % N);
   const int gy = n / g, gx = n % g;
-  const float* xb = x + (size_t)(b % Bx) * C * img * img;
+  const float* xb = x + (size_t)b * C * img * img;
   // gather the patch (c, p1, p2) and apply the strided conv as a pd x pd mat-vec
   float* t = s_t[wib];
   for (int i = lane; i < pd; i += 32) {
@@ -282,7 +283,6 @@ __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ x,
     q2 += (a * a + bb * bb) + (c * c + d * d);
   }
   const float rstd2 = rsqrtf(warp_sum(q2) * (1.0f / D) + LN_EPS);
-  float4* orow = reinterpret_cast<float4*>(out + (size_t)tok * D);
   const float4* prow = reinterpret_cast<const float4*>(w.pos + (size_t)n * D);
 #pragma unroll
   for (int j = 0; j < V; ++j) {
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ x,
     o.y = (e[j].y - mu2) * rstd2 * gm.y + bt.y + p.y;
     o.z = (e[j].z - mu2) * rstd2 * gm.z + bt.z + p.z;
     o.w = (e[j].w - mu2) * rstd2 * gm.w + bt.w + p.w;
-    orow[lane + 32 * j] = o;
+    for (int bb = b; bb < Bout; bb += Bx) reinterpret_cast<float4*>(out + ((size_t)bb * N + n) * D)[lane + 32 * j] = o;
   }
 }
 
@@ -382,7 +382,9 @@ int launch_embed(const float* x, int Bx, int Bout, int C, int img, int patch, in
   }
   TLD_CHECK(C * patch * patch <= 64, "embed: patch_dim (n_channels*patch^2) must be <= 64");
   TLD_CHECK(img % patch == 0, "embed: image_size must be divisible by patch_size");
-  const long long toks = (long long)Bout * (img / patch) * (img / patch);
+  TLD_CHECK(Bx > 0 && Bout % Bx == 0, "embed: the output batch must be a whole number of copies of the input batch");
+  TLD_CHECK(svp == nullptr || Bx == Bout, "embed: the training path embeds every image once");
+  const long long toks = (long long)Bx * (img / patch) * (img / patch);
   const int grid = int((toks + 7) / 8);
   switch (D / 128) {
 #define EM_CASE(V) \
@@ -1007,8 +1009,10 @@ __global__ void __launch_bounds__(256) outproj_kernel(const float* __restrict__ 
   }
 }
 
-// Fast path for patch_dim 16 (4 channels x 2x2): the [16, D] weight lives in shared memory, a warp keeps the token row in
-// registers and loops over tokens (persistent grid); lane o keeps output o.
+// Fast path for patch_dim 16 (4 channels x 2x2): the [16, D] weight lives in shared memory, a warp keeps FOUR token rows in
+// registers (every weight element read from shared memory feeds 4 tokens: the one-token version was shared-memory bound,
+// 96 LDS.128 per token) and loops over groups of tokens (persistent grid).  Four-row sums by a 6-shuffle transpose-reduce:
+// afterwards the 8 lanes with (bit4, bit3) = r hold the sum of token r; lane (r, l) keeps outputs l and l + 8.
 template <int V>
 __global__ void __launch_bounds__(256) outproj16_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, float* __restrict__ out,
@@ -1021,29 +1025,47 @@ __global__ void __launch_bounds__(256) outproj16_kernel(const float* __restrict_
   pdl_wait();
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = img / patch, N = g * g;
-  for (long long tok = (long long)blockIdx.x * 8 + wib; tok < T; tok += (long long)gridDim.x * 8) {
-    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)tok * D);
-    float4 xv[V];
+  const bool hi4 = lane & 16, hi3 = lane & 8;
+  const int my_r = (hi4 ? 2 : 0) + (hi3 ? 1 : 0), l3 = lane & 7;
+  const long long groups = (T + 3) / 4;
+  for (long long grp = (long long)blockIdx.x * 8 + wib; grp < groups; grp += (long long)gridDim.x * 8) {
+    float4 xv[4][V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) xv[j] = xr[lane + 32 * j];
-    float mine = 0.f;  // lane o ends up with output o
-#pragma unroll 1
+    for (int r = 0; r < 4; ++r) {
+      const long long tok = grp * 4 + r;
+      const float4* xr = reinterpret_cast<const float4*>(x + (size_t)(tok < T ? tok : T - 1) * D);
+#pragma unroll
+      for (int j = 0; j < V; ++j) xv[r][j] = xr[lane + 32 * j];
+    }
+    float mine[2] = {0.f, 0.f};   // outputs l3 and l3 + 8 of token my_r
+#pragma unroll
     for (int o = 0; o < 16; ++o) {
-      float a = 0.f;
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < V; ++j) {
         const float4 wv = reinterpret_cast<const float4*>(s_w + o * D)[lane + 32 * j];
-        a += xv[j].x * wv.x + xv[j].y * wv.y + xv[j].z * wv.z + xv[j].w * wv.w;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[r] += xv[r][j].x * wv.x + xv[r][j].y * wv.y + xv[r][j].z * wv.z + xv[r][j].w * wv.w;
       }
-      a = warp_sum(a);
-      if (lane == o) mine = a;
+      float k0 = hi4 ? a[2] : a[0], k1 = hi4 ? a[3] : a[1];
+      k0 += __shfl_xor_sync(0xffffffffu, hi4 ? a[0] : a[2], 16);
+      k1 += __shfl_xor_sync(0xffffffffu, hi4 ? a[1] : a[3], 16);
+      float k = hi3 ? k1 : k0;
+      k += __shfl_xor_sync(0xffffffffu, hi3 ? k0 : k1, 8);
+      k += __shfl_xor_sync(0xffffffffu, k, 4);
+      k += __shfl_xor_sync(0xffffffffu, k, 2);
+      k += __shfl_xor_sync(0xffffffffu, k, 1);
+      if ((o & 7) == l3) mine[o >> 3] = k;
     }
-    const float tot = mine;
-    const int o = lane;
-    if (lane < 16) {
+    const long long tok = grp * 4 + my_r;
+    if (tok < T) {
       const int b = int(tok / N), n = int(tok % N), gy = n / g, gx = n % g;
-      const int c = o / (patch * patch), p1 = (o / patch) % patch, p2 = o % patch;
-      out[((size_t)b * C + c) * img * img + (size_t)(gy * patch + p1) * img + gx * patch + p2] = tot + bias[o];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int o = l3 + 8 * u;
+        const int c = o / (patch * patch), p1 = (o / patch) % patch, p2 = o % patch;
+        out[((size_t)b * C + c) * img * img + (size_t)(gy * patch + p1) * img + gx * patch + p2] = mine[u] + bias[o];
+      }
     }
   }
 }
@@ -1054,8 +1076,8 @@ int launch_outproj(const float* x, const float* w, const float* b, float* out, i
   const long long toks = (long long)B * (img / patch) * (img / patch);
   if (C * patch * patch == 16 && D % 128 == 0 && D <= 768) {
     const int smem = 16 * D * 4;
-    long long nb = (toks + 7) / 8;
-    if (nb > 4LL * sm_count()) nb = 4LL * sm_count();
+    long long nb = (toks + 31) / 32;   // 8 warps x 4 tokens per CTA
+    if (nb > (long long)sm_count()) nb = sm_count();   // 194 registers: one CTA per SM
     switch (D / 128) {
 #define OP_CASE(V)                                                                                               \
   case V: {                                                                                                      \

@@ -13,7 +13,7 @@
 // The logits are formed from the fp32 row (the GEMM path rounds LN2(x) and q's operands to bf16).
 //
 // Layout: one warp = 4 rows (lane l holds columns 128 j + 4 l .. + 3 of each, j < V = D / 128, so its columns of block j
-// belong to head 2 j + (l >= 16)); a CTA walks a contiguous range of 32-row chunks and keeps the current sample's tables in
+// belong to head 2 j + (l >= 16)); a CTA walks a contiguous range of 4-row groups and keeps the current sample's tables in
 // shared memory: dl [H][D], v1, v0 - v1, gamma3, beta3, per-head sum(dl_h) and the beta constant.  Every dl element read
 // from shared memory feeds 4 rows (FMA : LDS.128 = 16 : 1); four-row reductions use a 6-shuffle transpose-reduce.
 // Bound: HBM (D * 10 bytes per row) with ~17 k FMA-pipe operations per row riding along.
@@ -106,8 +106,12 @@ __device__ __forceinline__ void bcast4(float mine, int lane, float (&out)[4]) {
   for (int r = 0; r < 4; ++r) out[r] = __shfl_sync(0xffffffffu, mine, (r >> 1) * 16 + (r & 1) * 8 + (lane & 7));
 }
 
+// 8 warps x 255 registers.  12 warps (168 registers: 250 B of spills at D = 768, more idle warps at the sample boundaries of a
+// CTA's range) measured slower: 75.5 against 68.6 us.
+__host__ __device__ constexpr int xl_warps(int V) { return 8; }
 template <int V>
-__global__ void __launch_bounds__(256, V <= 4 ? 2 : 1) ln_xattn_ln_kernel(XlArgs a) {
+__global__ void __launch_bounds__(xl_warps(V) * 32, 1) ln_xattn_ln_kernel(XlArgs a) {
+  constexpr int NW = xl_warps(V), NT = NW * 32;
   constexpr int D = V * 128, H = 2 * V, D4 = D / 4;
   extern __shared__ float4 xl_smem[];
   float4* dl = xl_smem;            // [H][D4]
@@ -115,41 +119,54 @@ __global__ void __launch_bounds__(256, V <= 4 ? 2 : 1) ln_xattn_ln_kernel(XlArgs
   float4* dv = v1 + D4;
   float4* g3 = dv + D4;
   float4* b3 = g3 + D4;
-  float4* rowbuf = b3 + D4;                        // [8 warps][4 rows][D4]: the warp's next rows, filled by a bulk copy
-  float* hs = reinterpret_cast<float*>(rowbuf + 8 * 4 * D4);   // [H] sum_c dl_h[c]
+  float4* rowbuf = b3 + D4;                        // [NW warps][4 rows][D4]: the warp's next rows, filled by a bulk copy
+  float* hs = reinterpret_cast<float*>(rowbuf + NW * 4 * D4);   // [H] sum_c dl_h[c]
   float* hc = hs + H;                              // [H] sum_c beta2[c] (u0 - u1)_h[c]
-  uint64_t* row_bar = reinterpret_cast<uint64_t*>(hc + H + (H & 1));   // [8]
+  uint64_t* row_bar = reinterpret_cast<uint64_t*>(hc + H + (H & 1));   // [NW]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_chunks = a.rows / 32;
-  const int c_begin = int((long long)n_chunks * blockIdx.x / gridDim.x), c_end = int((long long)n_chunks * (blockIdx.x + 1) / gridDim.x);
+  // work unit = group of 4 consecutive rows (one warp); a CTA owns a contiguous range of groups and walks it sample by
+  // sample (segment = the part of a sample inside the range): warp w takes groups seg + w, seg + w + NW, ...
+  const int n_groups = a.rows / 4, gps = a.n_tok / 4;   // groups per sample
+  const int G0 = int((long long)n_groups * blockIdx.x / gridDim.x), G1 = int((long long)n_groups * (blockIdx.x + 1) / gridDim.x);
   pdl_launch_dependents();
-  for (int i = threadIdx.x; i < D4; i += 256) {
+  for (int i = threadIdx.x; i < D4; i += NT) {
     g3[i] = __ldg(reinterpret_cast<const float4*>(a.g3) + i);
     b3[i] = __ldg(reinterpret_cast<const float4*>(a.b3) + i);
   }
-  if (threadIdx.x < 8) mbar_init(&row_bar[threadIdx.x], 1);
+  if (threadIdx.x < NW) mbar_init(&row_bar[threadIdx.x], 1);
   fence_mbar_init();
   __syncthreads();
   pdl_wait();
   float4* my_buf = rowbuf + warp * 4 * D4;
-  auto prefetch_rows = [&](int chunk) {   // lane 0: the 4 rows of this warp in `chunk` (4 D floats, contiguous)
-    mbar_expect_tx(&row_bar[warp], 4 * D * 4);
-    bulk_load_1d(smem_u32(my_buf), a.x + (size_t)(chunk * 32 + warp * 4) * D, 4 * D * 4, &row_bar[warp]);
+  auto seg_end_of = [&](int g) { const int e = (g / gps + 1) * gps; return e < G1 ? e : G1; };
+  auto first_from = [&](int s) {   // first group >= segment start s that belongs to this warp, or -1
+    while (s < G1) {
+      const int e = seg_end_of(s);
+      if (s + warp < e) return s + warp;
+      s = e;
+    }
+    return -1;
   };
-  if (lane == 0 && c_begin < c_end) prefetch_rows(c_begin);
+  auto next_of = [&](int g, int seg_end) { return g + NW < seg_end ? g + NW : first_from(seg_end); };
+  auto prefetch_rows = [&](int g) {   // lane 0: the 4 rows of group g (4 D floats, contiguous in x)
+    mbar_expect_tx(&row_bar[warp], 4 * D * 4);
+    bulk_load_1d(smem_u32(my_buf), a.x + (size_t)g * 4 * D, 4 * D * 4, &row_bar[warp]);
+  };
+  {
+    const int g = first_from(G0);
+    if (lane == 0 && g >= 0) prefetch_rows(g);
+  }
   uint32_t row_phase = 0;
   const float scale = 0.125f;   // 1 / sqrt(head_dim)
-  int cur_b = -1;
-  for (int chunk = c_begin; chunk < c_end; ++chunk) {
-    const int row0 = chunk * 32;
-    const int b = row0 / a.n_tok;
-    if (b != cur_b) {   // (re)build the sample's tables
+  for (int seg = G0; seg < G1;) {
+    const int seg_end = seg_end_of(seg);
+    const int b = seg / gps;
+    {   // build the sample's tables
       __syncthreads();  // every warp is done with the previous sample's tables
-      cur_b = b;
       const long long r0 = a.step_ptr ? (long long)(*a.step_ptr) : (long long)b;
       const float4* u0 = reinterpret_cast<const float4*>(a.uk0 + r0 * a.uk0_stride);
       const float4* u1 = reinterpret_cast<const float4*>(a.uk1 + (long long)b * a.uk1_stride);
-      for (int h = warp; h < H; h += 8) {   // warp = head: dl_h and its two constants
+      for (int h = warp; h < H; h += NW) {   // warp = head: dl_h and its two constants
         float s = 0.f, c = 0.f;
 #pragma unroll
         for (int jj = 0; jj < V; ++jj) {   // unrolled: all 4 V loads of the head in flight at once
@@ -171,15 +188,16 @@ __global__ void __launch_bounds__(256, V <= 4 ? 2 : 1) ln_xattn_ln_kernel(XlArgs
       }
       const float4* va = reinterpret_cast<const float4*>(a.kv0 + r0 * a.kv0_stride) + D4;
       const float4* vb = reinterpret_cast<const float4*>(a.kv1 + (long long)b * a.kv1_stride) + D4;
-      for (int i = threadIdx.x; i < D4; i += 256) {
+      for (int i = threadIdx.x; i < D4; i += NT) {
         const float4 p = __ldg(va + i), q = __ldg(vb + i);
         v1[i] = q;
         dv[i] = make_float4(p.x - q.x, p.y - q.y, p.z - q.z, p.w - q.w);
       }
       __syncthreads();
     }
-    // ---- 4 rows of this warp
-    const int row = row0 + warp * 4;
+    // ---- this warp's groups of the segment
+    for (int gw = seg + warp; gw < seg_end; gw += NW) {
+    const int row = gw * 4;
     float4 xv[4][V];
     float acc[4];
     mbar_wait(&row_bar[warp], row_phase);
@@ -195,7 +213,10 @@ __global__ void __launch_bounds__(256, V <= 4 ? 2 : 1) ln_xattn_ln_kernel(XlArgs
       acc[r] = s;
     }
     __syncwarp();   // every lane has its rows in registers: the buffer may be refilled
-    if (lane == 0 && chunk + 1 < c_end) prefetch_rows(chunk + 1);
+    {
+      const int gn = next_of(gw, seg_end);
+      if (lane == 0 && gn >= 0) prefetch_rows(gn);
+    }
     const float mean_mine = reduce4(acc, lane) * (1.f / D);
     float mean[4];
     bcast4(mean_mine, lane, mean);
@@ -214,15 +235,20 @@ __global__ void __launch_bounds__(256, V <= 4 ? 2 : 1) ln_xattn_ln_kernel(XlArgs
     float p0h[H];   // p0 of row (2 bit4 + bit3)(lane) for every head; broadcast when the columns are updated
 #pragma unroll
     for (int h = 0; h < H; ++h) {
+      float2 a2[4];   // packed fp32 FMA (FFMA2): half the issue slots of the dot products
 #pragma unroll
-      for (int r = 0; r < 4; ++r) acc[r] = 0.f;
+      for (int r = 0; r < 4; ++r) a2[r] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
         const float4 d = dl[h * D4 + lane + 32 * j];
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-          acc[r] = fmaf(xv[r][j].x, d.x, fmaf(xv[r][j].y, d.y, fmaf(xv[r][j].z, d.z, fmaf(xv[r][j].w, d.w, acc[r]))));
+        for (int r = 0; r < 4; ++r) {
+          a2[r] = ffma2(make_float2(xv[r][j].x, xv[r][j].y), make_float2(d.x, d.y), a2[r]);
+          a2[r] = ffma2(make_float2(xv[r][j].z, xv[r][j].w), make_float2(d.z, d.w), a2[r]);
+        }
       }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = a2[r].x + a2[r].y;
       const float tot = reduce4(acc, lane);
       const float dlt = rstd_mine * (tot - mean_mine * hs[h]) + hc[h];
       p0h[h] = 1.f / (1.f + __expf(-dlt * scale));
@@ -274,20 +300,23 @@ __global__ void __launch_bounds__(256, V <= 4 ? 2 : 1) ln_xattn_ln_kernel(XlArgs
         yr[lane + 32 * j] = o;
       }
     }
+    }   // groups of this warp
+    seg = seg_end;
   }
 }
 
-static size_t xl_smem_bytes(int D) {   // tables + 8 warps x 4 rows of prefetch buffer + per-head constants + 8 mbarriers
-  return (size_t)(D / 64) * D * 4 + 4 * (size_t)D * 4 + 32 * (size_t)D * 4 + 2 * (size_t)(D / 64 + 1) * 4 + 64 + 64;
+static size_t xl_smem_bytes(int D) {   // tables + 4 rows of prefetch buffer per warp + per-head constants + mbarriers
+  const int nw = xl_warps(D / 128);
+  return (size_t)(D / 64) * D * 4 + 4 * (size_t)D * 4 + nw * 4 * (size_t)D * 4 + 2 * (size_t)(D / 64 + 1) * 4 + nw * 8 + 64;
 }
 
-bool ln_xattn_ln_supported(int D, int n_tok) { return D % 128 == 0 && D >= 128 && D <= 1024 && n_tok % 32 == 0; }
+bool ln_xattn_ln_supported(int D, int n_tok) { return D % 128 == 0 && D >= 128 && D <= 1024 && n_tok % 4 == 0; }
 
 int launch_ln_xattn_ln(float* x, const float* g2, const float* b2, const float* g3, const float* b3, const float* uk0,
                        long long uk0_stride, const float* uk1, long long uk1_stride, const float* kv0, long long kv0_stride,
                        const float* kv1, long long kv1_stride, const int* step_ptr, bf16* y, int rows, int n_tok, int D,
                        cudaStream_t st) {
-  TLD_CHECK(ln_xattn_ln_supported(D, n_tok), "ln_xattn_ln: needs embed_dim % 128 == 0 (<= 1024) and tokens per sample % 32 == 0");
+  TLD_CHECK(ln_xattn_ln_supported(D, n_tok), "ln_xattn_ln: needs embed_dim % 128 == 0 (<= 1024) and tokens per sample % 4 == 0");
   TLD_CHECK(rows > 0 && rows % n_tok == 0, "ln_xattn_ln: rows must be whole samples");
   TLD_CHECK(x && g2 && b2 && g3 && b3 && uk0 && uk1 && kv0 && kv1 && y, "ln_xattn_ln: null argument");
   TLD_CHECK(uk0_stride % 4 == 0 && uk1_stride % 4 == 0 && kv0_stride % 4 == 0 && kv1_stride % 4 == 0 &&
@@ -297,22 +326,21 @@ int launch_ln_xattn_ln(float* x, const float* g2, const float* b2, const float* 
                   reinterpret_cast<uintptr_t>(b3)) & 15) == 0,
             "ln_xattn_ln: operands must be 16-byte aligned");
   XlArgs a{x, g2, b2, g3, b3, uk0, uk1, uk0_stride, uk1_stride, kv0, kv1, kv0_stride, kv1_stride, step_ptr, y, rows, n_tok};
-  const int n_chunks = rows / 32;
+  const int n_groups = rows / 4;
   const size_t smem = xl_smem_bytes(D);
-  int per_sm = 1;
   switch (D / 128) {
 #define XL_CASE(V)                                                                                                          \
   case V: {                                                                                                                 \
     static int occ = 0;                                                                                                     \
     if (!occ) {                                                                                                             \
       TLD_CUDA_OK(cudaFuncSetAttribute(ln_xattn_ln_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xl_smem_bytes(V * 128))); \
-      TLD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_xattn_ln_kernel<V>, 256, xl_smem_bytes(V * 128)));  \
+      TLD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln_xattn_ln_kernel<V>, xl_warps(V) * 32, xl_smem_bytes(V * 128)));  \
       if (occ < 1) occ = 1;                                                                                                 \
     }                                                                                                                       \
-    per_sm = occ;                                                                                                           \
-    const int slots = per_sm * sm_count();                                                                                  \
-    const int grid = n_chunks < slots ? n_chunks : slots;                                                                   \
-    if (launch_pdl(ln_xattn_ln_kernel<V>, dim3(grid), dim3(256), smem, st, a)) return 1;                                    \
+    const int slots = occ * sm_count();                                                                                     \
+    const int want = (n_groups + xl_warps(V) - 1) / xl_warps(V);                                                            \
+    const int grid = want < slots ? want : slots;                                                                           \
+    if (launch_pdl(ln_xattn_ln_kernel<V>, dim3(grid), dim3(xl_warps(V) * 32), smem, st, a)) return 1;                       \
   } break;
     XL_CASE(1) XL_CASE(2) XL_CASE(3) XL_CASE(4) XL_CASE(5) XL_CASE(6) XL_CASE(7) XL_CASE(8)
 #undef XL_CASE
