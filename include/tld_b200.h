@@ -173,6 +173,16 @@ TLD_API int tld_vae_add_bias(const uint16_t* x, const uint16_t* h, const float* 
  * out NHWC bf16 [batch,h,w,cout]; cin,cout multiples of 64, h*w multiple of 128. */
 TLD_API int tld_vae_conv3x3(const uint16_t* x, const uint16_t* w, const float* bias, uint16_t* out, int batch, int h,
                             int w_px, int cin, int cout, void* stream);
+/* The same convolution with the ResnetBlock tail in its epilogue: out = conv(x) + bias + residual (residual NHWC bf16
+ * [batch,h,w,cout] or NULL), and - if gn_partials is not NULL - the GroupNorm statistics partials of the STORED output,
+ * gn_partials fp32 [batch*h*w/32, cout/4, 2] = (sum, sum of squares) per 32-pixel slab and 4-channel quad, for
+ * tld_vae_group_norm_from_conv.  bias must not be NULL here. */
+TLD_API int tld_vae_conv3x3_fused(const uint16_t* x, const uint16_t* w, const float* bias, uint16_t* out, int batch, int h,
+                                  int w_px, int cin, int cout, const uint16_t* residual, float* gn_partials, void* stream);
+/* act(GroupNorm(x)) with the statistics taken from the producing convolution's partials (x is read once, not twice) */
+TLD_API int tld_vae_group_norm_from_conv(const uint16_t* x, const float* conv_partials, const float* gamma, const float* beta,
+                                         uint16_t* y, int batch, int hw, int channels, int groups, float eps, int silu,
+                                         void* stream);
 /* decoder.conv_out (3x3 'same', 128 -> 3 channels): an HBM-bound direct convolution on the CUDA cores (nothing for a tensor core
  * to do with 3 output channels).  x NHWC bf16 [batch,h,w,128] (device); w_host [3,128,3,3] and b_host [3] are HOST fp32 arrays
  * (the 3456 weights travel in the kernel-parameter constant bank); out fp32 NCHW [batch,3,h,w] (device) = the final image. */

@@ -372,3 +372,51 @@ def test_conv_out3_direct_kernel(B, H, W):
     torch.cuda.synchronize()
     assert torch.isfinite(out).all()
     assert rel_fro(out, ref) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,cin,cout", [(2, 16, 16, 128, 128), (1, 32, 32, 256, 128), (3, 16, 32, 128, 256), (1, 16, 16, 512, 512)])
+def test_conv3x3_fused_residual_and_groupnorm_partials(B, H, W, cin, cout):
+    """conv + bias + shortcut add in the GEMM epilogue, and the GroupNorm partials of the stored output (the consumer reads
+    the tensor once): against fp32 torch, and the normalisation against the two-pass kernel on the same tensor"""
+    from transformer_latent_diffusion_b200 import _lib
+
+    L = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(B * 7 + cin + cout)
+    x = torch.randn(B, cin, H, W, device="cuda", generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+    res = torch.randn(B, cout, H, W, device="cuda", generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (3 * cin ** 0.5)).bfloat16()
+    bias = torch.randn(cout, device="cuda", generator=g)
+    wp = w.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+    y = torch.empty_like(res)
+    part = torch.full((B * H * W // 32, cout // 4, 2), float("nan"), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.tld_vae_conv3x3_fused(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), y.data_ptr(), B, H, W, cin, cout,
+                                       res.data_ptr(), part.data_ptr(), st), "conv3x3_fused")
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), bias.double(), padding=1) + res.double()
+    assert rel_fro(y.double(), ref) < 4e-3
+    # partials: per (image, group) sums of the STORED values
+    assert torch.isfinite(part).all()
+    cpg = cout // 32
+    ps = part.view(B, H * W // 32, 32, cpg // 4, 2).double().sum(dim=(1, 3))            # [B, 32 groups, 2]
+    yv = y.double().view(B, 32, cpg, H * W)
+    assert torch.allclose(ps[..., 0], yv.sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(ps[..., 1], (yv * yv).sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
+    # the normalisation from the partials == the two-pass kernel on the same tensor
+    gamma = torch.randn(cout, device="cuda", generator=g) * 0.2 + 1
+    beta = torch.randn(cout, device="cuda", generator=g) * 0.2
+    a, b2 = torch.empty_like(y), torch.empty_like(y)
+    _lib.check(L.tld_vae_group_norm_from_conv(y.data_ptr(), part.data_ptr(), gamma.data_ptr(), beta.data_ptr(), a.data_ptr(), B,
+                                              H * W, cout, 32, 1e-6, 1, st), "gn_from_conv")
+    _lib.check(L.tld_vae_group_norm(y.data_ptr(), None, gamma.data_ptr(), beta.data_ptr(), b2.data_ptr(), B, H * W, cout, 32, 1e-6,
+                                    1, st), "gn")
+    torch.cuda.synchronize()
+    assert rel_fro(a.float(), b2.float()) < 2e-3
+    # without residual / partials the plain entry point gives the same convolution
+    y2 = torch.empty_like(y)
+    _lib.check(L.tld_vae_conv3x3_fused(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), y2.data_ptr(), B, H, W, cin, cout, None, None,
+                                       st), "conv3x3_fused")
+    y3 = torch.empty_like(y)
+    _lib.check(L.tld_vae_conv3x3(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), y3.data_ptr(), B, H, W, cin, cout, st), "conv3x3")
+    torch.cuda.synchronize()
+    assert torch.equal(y2, y3)

@@ -141,7 +141,7 @@ int launch_advance_step(int* step_ptr, cudaStream_t st);
 
 // 3x3 'same' conv as implicit GEMM: x NHWC bf16, w bf16 [Cout, 9*Cin] with K order (ky,kx,cin), bias fp32 or null
 int launch_conv3x3(const bf16* x, const bf16* w, const float* bias, bf16* out, int B, int H, int W, int Cin, int Cout,
-                   cudaStream_t st);
+                   cudaStream_t st, const bf16* resid = nullptr, float* gn_part = nullptr);
 // MLPSepConv front half fused (gemm_dwconv.cu): g = GELU(dwconv3x3(A W^T [LayerNorm-folded] + c) + dw_b) for 16x16-token samples
 int launch_gemm_up_dwconv_gelu(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const float* col_c,
                                const float* col_s, const float2* row_part, int n_part, float ln_eps, const float* dw_w9,

@@ -156,7 +156,7 @@ static int dispatch(int ctas, int bn, int epi, const CUtensorMap& ta, const CUte
 // 3x3 'same' convolution as an implicit GEMM on the tcgen05 core: x NHWC bf16 [B,H,W,Cin], w bf16 [Cout, 9*Cin]
 // (K order = (ky, kx, cin)), bias fp32 [Cout] -> out NHWC bf16 [B,H,W,Cout].
 int launch_conv3x3(const bf16* x, const bf16* w, const float* bias, bf16* out, int B, int H, int W, int Cin, int Cout,
-                   cudaStream_t st) {
+                   cudaStream_t st, const bf16* resid, float* gn_part) {
   TLD_CHECK(Cin % 64 == 0 && Cout % 64 == 0, "conv3x3: Cin and Cout must be multiples of 64");
   TLD_CHECK((H * W) % 128 == 0, "conv3x3: H*W must be a multiple of 128");
   const int w_box = W < 128 ? W : 128;
@@ -172,11 +172,16 @@ int launch_conv3x3(const bf16* x, const bf16* w, const float* bias, bf16* out, i
   if (make_tmap_nhwc(&ta, x, B, H, W, Cin, w_box, h_box)) return 1;
   if (make_tmap_2d(&tb, w, false, N, K, K, bn / ctas)) return 1;
   if (make_tmap_2d(&tc, out, false, M, N, N, 32)) return 1;
+  TLD_CHECK((resid == nullptr && gn_part == nullptr) || bias != nullptr, "conv3x3: the residual / GroupNorm-partials epilogue needs a bias");
+  TLD_CHECK((reinterpret_cast<uintptr_t>(resid) & 15) == 0 && (reinterpret_cast<uintptr_t>(gn_part) & 7) == 0,
+            "conv3x3: residual must be 16-byte aligned");
   GemmEpi ep{};
   ep.bias = bias;
   ep.conv_cpb = Cin / 64;
   ep.conv_h = H;
   ep.conv_w = W;
+  ep.resid = resid;
+  ep.gn_part = gn_part;
   return dispatch(ctas, bn, bias ? EPI_BIAS_BF16 : EPI_BF16, ta, tb, tc, tc, (int)M, N, K, ep, st);
 }
 

@@ -76,7 +76,26 @@ struct GemmEpi {
   // producer side (EPI_*_LNP): x_in == the fp32 output (read thread = row before it is overwritten), part_out [M, N / 32]
   const float* x_in;
   float2* part_out;
+  // EPI_BIAS_BF16 extras (VAE convolutions): resid = bf16 [M, N] added before the rounding (ResnetBlock shortcut); gn_part =
+  // [M / 32, N / 4] (sum, sum of squares) of the STORED bf16 values per 32-row slab and 4-channel quad: the GroupNorm that
+  // consumes this tensor sums them instead of reading it once more
+  const __nv_bfloat16* resid;
+  float* gn_part;
 };
+
+// 32 per-lane values -> lane L ends with the warp total of value L (16 + 8 + 4 + 2 + 1 shuffles)
+__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool hi = lane & w;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float keep = hi ? v[w + i] : v[i], send = hi ? v[i] : v[w + i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return v[0];
+}
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 bf16 = 128 B = one swizzle row
@@ -596,11 +615,25 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tmem_ld_wait();
           const int col = n0 + ch * 64;
           uint32_t o[32];
+          [[maybe_unused]] uint32_t rw[32];   // residual: the 64 bf16 of this row under the chunk
+          [[maybe_unused]] bool has_res = false;
+          if constexpr (EPI == EPI_BIAS_BF16) {
+            has_res = ep.resid != nullptr && row < M && col + 63 < N;
+            if (has_res) {
+              const uint4* rp = reinterpret_cast<const uint4*>(ep.resid + (size_t)row * N + col);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(&rw[4 * j]) = __ldg(rp + j);
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float f0 = __uint_as_float(ra[2 * i]), f1 = __uint_as_float(ra[2 * i + 1]);
             float g0 = __uint_as_float(rb[2 * i]), g1 = __uint_as_float(rb[2 * i + 1]);
             if constexpr (EPI == EPI_BIAS_BF16) {
+              if (has_res) {
+                f0 += __uint_as_float(rw[i] << 16); f1 += __uint_as_float(rw[i] & 0xffff0000u);
+                g0 += __uint_as_float(rw[16 + i] << 16); g1 += __uint_as_float(rw[16 + i] & 0xffff0000u);
+              }
               // N is a multiple of 32: a ragged last group (N % 64 == 32) still gets its first half's bias
               if (col + 31 < N) {
                 const float2 b0 = __ldg(reinterpret_cast<const float2*>(ep.bias + col) + i);
@@ -625,6 +658,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             o[i] = pack_bf16x2(f0, f1);
             o[16 + i] = pack_bf16x2(g0, g1);
+          }
+          if constexpr (EPI == EPI_BIAS_BF16) {
+            if (ep.gn_part != nullptr && col + 63 < N) {   // GroupNorm partials of the rounded values: 16 quads x (sum, sum of squares)
+              float v[32];
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const uint32_t w0 = o[(q < 8 ? 0 : 16) + 2 * (q & 7)], w1 = o[(q < 8 ? 0 : 16) + 2 * (q & 7) + 1];
+                const float a = __uint_as_float(w0 << 16), b = __uint_as_float(w0 & 0xffff0000u);
+                const float c = __uint_as_float(w1 << 16), d = __uint_as_float(w1 & 0xffff0000u);
+                const bool live = row < M;
+                v[2 * q] = live ? (a + b) + (c + d) : 0.f;
+                v[2 * q + 1] = live ? (a * a + b * b) + (c * c + d * d) : 0.f;
+              }
+              const float tot = warp_transpose_reduce32(v, lane);   // lane L: quad L / 2, L & 1 ? sum of squares : sum
+              ep.gn_part[((size_t)(slab_row >> 5) * (N >> 2) + (col >> 2)) * 2 + lane] = tot;
+            }
           }
           uint8_t* slab = slab_acquire();
           stage_row(slab, lane, o);

@@ -255,6 +255,66 @@ int launch_gn_act(const bf16* x, const float* pre_bias, const float* gamma, cons
   return 0;
 }
 
+// GroupNorm whose statistics partials came out of the producing convolution's epilogue (gemm_tcgen05.cuh, EPI_BIAS_BF16 with
+// gn_part): qpart [B * HW / 32 slabs][C / 4 quads] (sum, sum of squares) -> one (sum, sum of squares) per (image, group),
+// then the ordinary apply pass.  The tensor is read once instead of twice; the reduction order is fixed (deterministic).
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const float2* __restrict__ qpart, float2* __restrict__ out,
+                                                          int slabs_per_image, int Q, int groups) {
+  __shared__ double s_s[256], s_q[256];
+  const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;   // block blk sums slabs [blk * per, (blk + 1) * per)
+  const int per = (slabs_per_image + nblk - 1) / nblk;
+  const int i0 = blk * per, i1 = min(slabs_per_image, i0 + per);
+  const int quad = threadIdx.x % Q, sub = threadIdx.x / Q, nsub = 256 / Q;
+  double s = 0.0, q = 0.0;
+  const float2* p = qpart + (size_t)b * slabs_per_image * Q + quad;
+  for (int i = i0 + sub; i < i1; i += nsub) {
+    const float2 v = p[(size_t)i * Q];
+    s += v.x;
+    q += v.y;
+  }
+  s_s[threadIdx.x] = s;
+  s_q[threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.x < groups) {   // group g = quads [g * qpg, (g + 1) * qpg) x all sub-lanes, summed in a fixed order
+    const int qpg = Q / groups;
+    double ts = 0.0, tq = 0.0;
+    for (int u = 0; u < nsub; ++u)
+      for (int k = 0; k < qpg; ++k) {
+        ts += s_s[u * Q + threadIdx.x * qpg + k];
+        tq += s_q[u * Q + threadIdx.x * qpg + k];
+      }
+    out[((size_t)b * nblk + blk) * groups + threadIdx.x] = make_float2((float)ts, (float)tq);
+  }
+}
+
+int launch_gn_act_from_partials(const bf16* x, const float* qpart, const float* gamma, const float* beta, bf16* y, int B, int HW,
+                                int C, int groups, float eps, int silu, cudaStream_t st) {
+  TLD_CHECK(C % 8 == 0 && C <= 512 && (256 % (C / 8)) == 0, "group_norm: channels must be 128/256/512-like (C/8 divides 256)");
+  TLD_CHECK(groups <= 64 && C % groups == 0 && (C / groups) % 4 == 0, "group_norm: bad group configuration");
+  TLD_CHECK(B <= 65535 && HW % 32 == 0 && qpart != nullptr, "group_norm: conv-epilogue partials need H*W % 32 == 0");
+  const int Q = C / 4;
+  TLD_CHECK(Q <= 256 && 256 % Q == 0 && Q % groups == 0, "group_norm: bad quad layout");
+  // split every image's slabs over enough blocks to fill the machine (the apply kernel sums the nsplit partials per group)
+  int nsplit = (2 * sm_count() + B - 1) / B;
+  if (nsplit > HW / 32 / 8) nsplit = HW / 32 / 8;
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > 64) nsplit = 64;
+  float2* stats = reinterpret_cast<float2*>(device_scratch(SCR_GROUPNORM, 2 * (size_t)B * nsplit * groups));
+  if (!stats) return 1;
+  gn_finalize_kernel<<<dim3(nsplit, B), 256, 0, st>>>(reinterpret_cast<const float2*>(qpart), stats, HW / 32, Q, groups);
+  TLD_CUDA_OK(cudaGetLastError());
+  int nblk = (HW + 2047) / 2048;
+  const int want = (4 * sm_count() + B - 1) / B;
+  if (nblk < want) nblk = want;
+  int ppb = (HW + nblk - 1) / nblk;
+  const int pstride = 256 / (C / 8);
+  ppb = ((ppb + pstride - 1) / pstride) * pstride;
+  nblk = (HW + ppb - 1) / ppb;
+  gn_apply_kernel<<<dim3(nblk, B), 256, 0, st>>>(x, nullptr, stats, nsplit, gamma, beta, y, HW, C, groups, eps, silu, ppb);
+  TLD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int launch_upsample2x(const bf16* x, bf16* y, int B, int H, int W, int C, cudaStream_t st) {
   TLD_CHECK(C % 8 == 0, "upsample: channels must be a multiple of 8");
   const long long total = (long long)B * H * W * (C / 8);
@@ -396,6 +456,21 @@ __attribute__((visibility("default"))) int tld_vae_group_norm(const uint16_t* x,
                                                               int silu, void* stream) {
   return tld::launch_gn_act(reinterpret_cast<const tld::bf16*>(x), pre_bias, gamma, beta, reinterpret_cast<tld::bf16*>(y),
                             batch, hw, channels, groups, eps, silu, reinterpret_cast<cudaStream_t>(stream));
+}
+__attribute__((visibility("default"))) int tld_vae_group_norm_from_conv(const uint16_t* x, const float* conv_partials,
+                                                                        const float* gamma, const float* beta, uint16_t* y,
+                                                                        int batch, int hw, int channels, int groups,
+                                                                        float eps, int silu, void* stream) {
+  return tld::launch_gn_act_from_partials(reinterpret_cast<const tld::bf16*>(x), conv_partials, gamma, beta,
+                                          reinterpret_cast<tld::bf16*>(y), batch, hw, channels, groups, eps, silu,
+                                          reinterpret_cast<cudaStream_t>(stream));
+}
+__attribute__((visibility("default"))) int tld_vae_conv3x3_fused(const uint16_t* x, const uint16_t* w, const float* bias,
+                                                                 uint16_t* out, int batch, int h, int w_px, int cin, int cout,
+                                                                 const uint16_t* residual, float* gn_partials, void* stream) {
+  return tld::launch_conv3x3(reinterpret_cast<const tld::bf16*>(x), reinterpret_cast<const tld::bf16*>(w), bias,
+                             reinterpret_cast<tld::bf16*>(out), batch, h, w_px, cin, cout,
+                             reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const tld::bf16*>(residual), gn_partials);
 }
 __attribute__((visibility("default"))) int tld_vae_add_bias(const uint16_t* x, const uint16_t* h, const float* bias,
                                                             uint16_t* out, long long numel, int channels, void* stream) {

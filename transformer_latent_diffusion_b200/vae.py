@@ -104,6 +104,7 @@ class AutoencoderKLDecoder(nn.Module):
         self.allow_aten = allow_aten  # test-only: run layers without a libtld_b200 kernel on the plain ATen graph
         self.force_aten = False       # test-only (needs allow_aten): skip the kernels everywhere = torch's own bf16 graph
         self.own_launches = 0  # libtld_b200 kernels launched by decode() so far (bench.py's gpu_launches)
+        self.fuse_gn_stats = True  # GroupNorm statistics partials + shortcut add in the producing conv's epilogue
         self._layout = vae_param_layout(latent_ch, block_out)
         for key, shape in self._layout.items():
             if key.endswith("weight") and len(shape) == 1:
@@ -233,7 +234,8 @@ class AutoencoderKLDecoder(nn.Module):
         return (self._on_kernels(x) and kh == 3 and kw == 3 and cin % 64 == 0 and cout % 64 == 0
                 and (H * W) % 128 == 0 and 128 % wb == 0 and W % wb == 0 and H % (128 // wb) == 0)
 
-    def _conv(self, x, name, pad, bias=True):
+    def _conv(self, x, name, pad, bias=True, residual=None):
+        """``residual`` (own 3x3 convolutions only): added in the GEMM epilogue before the rounding (ResnetBlock shortcut)."""
         if pad == 1 and self._own_conv_ok(x, name):
             from . import _lib
 
@@ -251,10 +253,25 @@ class AutoencoderKLDecoder(nn.Module):
             B, _, H, W = x.shape
             y = torch.empty((B, cout, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
             bp = self._f32(name + ".bias", x.device).data_ptr() if bias else None
+            if bias and self.fuse_gn_stats and cout % GN_GROUPS == 0 and (cout // GN_GROUPS) % 4 == 0:
+                # epilogue extras: the shortcut add, and the GroupNorm statistics partials of the stored output - whoever
+                # normalises this tensor next (norm2, the next block's norm1, conv_norm_out) reads it once instead of twice
+                part = torch.empty((B * H * W // 32, cout // 4, 2), device=x.device, dtype=torch.float32)
+                rp = None
+                if residual is not None:
+                    residual = residual.contiguous(memory_format=torch.channels_last)
+                    assert residual.shape == y.shape and residual.dtype == y.dtype
+                    rp = residual.data_ptr()
+                _lib.check(_lib.load().tld_vae_conv3x3_fused(x.data_ptr(), wp.data_ptr(), bp, y.data_ptr(), B, H, W, cin, cout, rp,
+                                                             part.data_ptr(), _lib.current_stream_ptr(x.device)),
+                           "tld_vae_conv3x3_fused")
+                y._tld_gn_part = part   # consumed by _group_norm if it is handed exactly this tensor object
+                self.own_launches += 1
+                return y
             _lib.check(_lib.load().tld_vae_conv3x3(x.data_ptr(), wp.data_ptr(), bp, y.data_ptr(), B, H, W, cin, cout,
                                                    _lib.current_stream_ptr(x.device)), "tld_vae_conv3x3")
             self.own_launches += 1
-            return y
+            return y if residual is None else self._add_bias(residual, y)
         w = self._p(name + ".weight")
         if pad == 1 and bias and w.shape[2] == 3 and self._kernel_map_ok(x):          # thin 3x3: channels padded to 64
             return self._conv3x3_padded(x, name)[:, :w.shape[0]]
@@ -287,8 +304,16 @@ class AutoencoderKLDecoder(nn.Module):
         if self._fusable(x):
             from . import _lib
 
+            part = getattr(x, "_tld_gn_part", None)
             x = x.contiguous(memory_format=torch.channels_last)
             y = torch.empty_like(x)  # keeps the NHWC strides
+            if part is not None and pre_bias is None and part.shape[0] * 32 == x.shape[0] * x.shape[2] * x.shape[3]:
+                _lib.check(_lib.load().tld_vae_group_norm_from_conv(
+                    x.data_ptr(), part.data_ptr(), self._f32(name + ".weight", x.device).data_ptr(),
+                    self._f32(name + ".bias", x.device).data_ptr(), y.data_ptr(), x.shape[0], x.shape[2] * x.shape[3], Cc,
+                    GN_GROUPS, GN_EPS, int(silu), _lib.current_stream_ptr(x.device)), "tld_vae_group_norm_from_conv")
+                self.own_launches += 2  # finalize + apply
+                return y
             pb = self._f32(pre_bias + ".bias", x.device).data_ptr() if pre_bias else None
             _lib.check(_lib.load().tld_vae_group_norm(
                 x.data_ptr(), pb, self._f32(name + ".weight", x.device).data_ptr(),
@@ -336,10 +361,10 @@ class AutoencoderKLDecoder(nn.Module):
         if self._own_conv_ok(x, name + ".conv1"):
             # tcgen05 implicit-GEMM convs: the bias is part of the GEMM epilogue
             h = self._conv(self._group_norm(x, name + ".norm1", True), name + ".conv1", 1)
-            h = self._conv(self._group_norm(h, name + ".norm2", True), name + ".conv2", 1)
             if (name + ".conv_shortcut.weight") in self._layout:
                 x = self._conv(x, name + ".conv_shortcut", 0)
-            return self._add_bias(x, h)
+            # the shortcut add rides in conv2's epilogue (and so do the statistics of the block's output for the next norm)
+            return self._conv(self._group_norm(h, name + ".norm2", True), name + ".conv2", 1, residual=x)
         # library convs: their biases are folded into the next fused kernel (GroupNorm input / residual add)
         h = self._conv(self._group_norm(x, name + ".norm1", True), name + ".conv1", 1, bias=False)
         h = self._conv(self._group_norm(h, name + ".norm2", True, pre_bias=name + ".conv1"), name + ".conv2", 1, bias=False)
@@ -520,6 +545,7 @@ class AutoencoderKLEncoder(AutoencoderKLDecoder):
         self.allow_aten = allow_aten
         self.force_aten = False
         self.own_launches = 0
+        self.fuse_gn_stats = True
         self._layout = vae_encoder_param_layout(latent_ch, block_out)
         for key, shape in self._layout.items():
             if key.endswith("weight") and len(shape) == 1:
