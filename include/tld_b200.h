@@ -183,6 +183,10 @@ TLD_API int tld_vae_conv3x3_fused(const uint16_t* x, const uint16_t* w, const fl
 TLD_API int tld_vae_group_norm_from_conv(const uint16_t* x, const float* conv_partials, const float* gamma, const float* beta,
                                          uint16_t* y, int batch, int hw, int channels, int groups, float eps, int silu,
                                          void* stream);
+/* softmax(q k^T / sqrt(channels)) v of the mid-block attention (ONE head as wide as the channel count): q, k, v, out bf16
+ * [batch, n_tok, channels] (rows = pixels); per image a tcgen05 GEMM, a row softmax and a tcgen05 GEMM.  n_tok, channels % 64 == 0. */
+TLD_API int tld_vae_attention_core(const uint16_t* q, const uint16_t* k, const uint16_t* v, uint16_t* out, int batch, int n_tok,
+                                   int channels, void* stream);
 /* decoder.conv_out (3x3 'same', 128 -> 3 channels): an HBM-bound direct convolution on the CUDA cores (nothing for a tensor core
  * to do with 3 output channels).  x NHWC bf16 [batch,h,w,128] (device); w_host [3,128,3,3] and b_host [3] are HOST fp32 arrays
  * (the 3456 weights travel in the kernel-parameter constant bank); out fp32 NCHW [batch,3,h,w] (device) = the final image. */

@@ -420,3 +420,19 @@ def test_conv3x3_fused_residual_and_groupnorm_partials(B, H, W, cin, cout):
     _lib.check(L.tld_vae_conv3x3(x.data_ptr(), wp.data_ptr(), bias.data_ptr(), y3.data_ptr(), B, H, W, cin, cout, st), "conv3x3")
     torch.cuda.synchronize()
     assert torch.equal(y2, y3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,n,C", [(2, 256, 128), (3, 1024, 512), (1, 64, 64)])
+def test_vae_attention_core(B, n, C):
+    """mid-block attention core (one C-wide head) on the library's GEMM + row softmax vs fp32 torch"""
+    from transformer_latent_diffusion_b200 import _lib
+
+    g = torch.Generator(device="cuda").manual_seed(n + C)
+    q, k, v = (torch.randn(B, n, C, device="cuda", generator=g).bfloat16() for _ in range(3))
+    q = q * 2.0
+    o = torch.empty_like(q)
+    _lib.check(_lib.load().tld_vae_attention_core(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, n, C,
+                                                  torch.cuda.current_stream().cuda_stream), "vae_attention")
+    ref = torch.softmax(q.double() @ k.double().transpose(1, 2) / C ** 0.5, -1) @ v.double()
+    assert rel_fro(o.double(), ref) < 6e-3

@@ -72,6 +72,7 @@ PROTOTYPES = {
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "tld_vae_group_norm_from_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                                C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]),
+    "tld_vae_attention_core": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tld_vae_conv_out3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tld_vae_upsample2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tld_latent_quantize": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_float, C.c_void_p]),

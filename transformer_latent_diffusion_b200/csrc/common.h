@@ -29,7 +29,7 @@ const char* last_error();
 int sm_count();
 // Grow-only fp32 scratch buffer, one per (current device, slot): reduction partials of the backward / GroupNorm kernels.
 // Per device so that handles on different GPUs of one process never share a pointer; returns nullptr on failure.
-enum ScratchSlot { SCR_COLSUM = 0, SCR_LN_BWD, SCR_DWCONV_DW, SCR_SPLIT_K, SCR_GROUPNORM, SCR_ATTN_BWD, SCR_COUNT };
+enum ScratchSlot { SCR_COLSUM = 0, SCR_LN_BWD, SCR_DWCONV_DW, SCR_SPLIT_K, SCR_GROUPNORM, SCR_ATTN_BWD, SCR_VAE_ATTN, SCR_COUNT };
 float* device_scratch(ScratchSlot slot, size_t n_floats);
 void set_pdl(int v);  // 1 = launch the step kernels with programmatic dependent launch, 0 = plain launches (default)
 

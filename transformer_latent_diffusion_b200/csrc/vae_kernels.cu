@@ -315,6 +315,45 @@ int launch_gn_act_from_partials(const bf16* x, const float* qpart, const float* 
   return 0;
 }
 
+// Mid-block attention core (one head as wide as the channel count, diffusers Attention with heads = 1): per image
+// S = Q K^T (tcgen05 GEMM, fp32 out) -> P = softmax(S / sqrt(C)) (row kernel, bf16) -> O = P V (tcgen05 GEMM with V as the
+// [K, N]-stored operand).  1024 tokens x 512 channels per image: 3 small launches per image, ~1 ms per 64-image decode.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, bf16* __restrict__ p, int rows, int cols,
+                                                           float scale_log2e) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* sr = s + (size_t)row * cols;
+  float mx = -INFINITY;
+  for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, sr[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int c = lane; c < cols; c += 32) sum += exp2f((sr[c] - mx) * scale_log2e);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.f / sum;
+  bf16* pr = p + (size_t)row * cols;
+  for (int c = lane; c < cols; c += 32) pr[c] = __float2bfloat16(exp2f((sr[c] - mx) * scale_log2e) * inv);
+}
+
+int launch_vae_attention_core(const bf16* q, const bf16* k, const bf16* v, bf16* out, int B, int n, int C, cudaStream_t st) {
+  TLD_CHECK(q && k && v && out && B > 0, "vae_attention: null argument");
+  TLD_CHECK(n % 64 == 0 && C % 64 == 0, "vae_attention: tokens and channels must be multiples of 64");
+  float* scr = device_scratch(SCR_VAE_ATTN, (size_t)n * n + (size_t)n * n / 2);
+  if (!scr) return 1;
+  float* s = scr;
+  bf16* p = reinterpret_cast<bf16*>(scr + (size_t)n * n);
+  const float scale_log2e = 1.4426950408889634f / sqrtf((float)C);
+  for (int b = 0; b < B; ++b) {
+    const size_t off = (size_t)b * n * C;
+    if (launch_gemm(4 /* EPI_F32 */, q + off, C, k + off, C, n, n, C, s, n, nullptr, nullptr, st)) return 1;
+    softmax_rows_kernel<<<(n + 7) / 8, 256, 0, st>>>(s, p, n, n, scale_log2e);
+    TLD_CUDA_OK(cudaGetLastError());
+    if (launch_gemm_nn(0 /* EPI_BF16 */, p, n, v + off, C, n, C, n, out + off, C, st)) return 1;
+  }
+  return 0;
+}
+
 int launch_upsample2x(const bf16* x, bf16* y, int B, int H, int W, int C, cudaStream_t st) {
   TLD_CHECK(C % 8 == 0, "upsample: channels must be a multiple of 8");
   const long long total = (long long)B * H * W * (C / 8);
@@ -471,6 +510,13 @@ __attribute__((visibility("default"))) int tld_vae_conv3x3_fused(const uint16_t*
   return tld::launch_conv3x3(reinterpret_cast<const tld::bf16*>(x), reinterpret_cast<const tld::bf16*>(w), bias,
                              reinterpret_cast<tld::bf16*>(out), batch, h, w_px, cin, cout,
                              reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const tld::bf16*>(residual), gn_partials);
+}
+__attribute__((visibility("default"))) int tld_vae_attention_core(const uint16_t* q, const uint16_t* k, const uint16_t* v,
+                                                                  uint16_t* out, int batch, int n_tok, int channels,
+                                                                  void* stream) {
+  return tld::launch_vae_attention_core(reinterpret_cast<const tld::bf16*>(q), reinterpret_cast<const tld::bf16*>(k),
+                                        reinterpret_cast<const tld::bf16*>(v), reinterpret_cast<tld::bf16*>(out), batch, n_tok,
+                                        channels, reinterpret_cast<cudaStream_t>(stream));
 }
 __attribute__((visibility("default"))) int tld_vae_add_bias(const uint16_t* x, const uint16_t* h, const float* bias,
                                                             uint16_t* out, long long numel, int channels, void* stream) {

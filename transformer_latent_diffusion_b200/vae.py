@@ -8,15 +8,15 @@ diffusers/SDXL-VAE structure with diffusers-compatible ``state_dict`` keys (``po
 ``decoder.conv_out``) so the real checkpoint loads when it is available, and is checked against the independent
 fp32 restatement in ``oracle/vae_oracle.py`` with random weights.
 
-STATUS: on CUDA/bf16 every layer runs on libtld_b200 kernels.  GroupNorm(+SiLU), nearest-2x upsample and the residual adds
-are hand-written row-wise kernels (``csrc/vae_kernels.cu``); every 3x3 convolution is an implicit GEMM on the tcgen05 GEMM
-core (``tld_vae_conv3x3``: 4-D TMA boxes shifted per tap, zero fill = padding) - the thin ones (conv_in 4 -> 512, conv_out
+STATUS: on CUDA/bf16 every layer runs on libtld_b200 kernels.  GroupNorm(+SiLU) and nearest-2x upsample are hand-written
+row-wise kernels (``csrc/vae_kernels.cu``); every 3x3 convolution is an implicit GEMM on the tcgen05 GEMM core
+(``tld_vae_conv3x3_fused``: 4-D TMA boxes shifted per tap, zero fill = padding; the ResnetBlock shortcut add and the GroupNorm
+statistics partials of its output ride in the epilogue) - the thin ones (conv_in 4 -> 512, conv_out
 128 -> 3, the encoder's 3 -> 128 / 512 -> 8) with their channel count zero-padded to 64; the 1x1 convolutions (shortcuts,
 post_quant_conv / quant_conv) and the q/k/v/out projections of the mid-block attention are plain tcgen05 GEMMs (``tld_op_gemm``
-with the bias epilogue); the encoder's stride-2 convolutions are the stride-1 kernel followed by a 2x sub-sampling.  The ONE
-library call left is the softmax(QK^T)V core of the single 512-wide head of the mid-block attention
-(``F.scaled_dot_product_attention``, < 0.5 % of the FLOPs; the tcgen05 attention kernel of this package is built for 64-wide
-heads).  There is NO silent fallback: a CUDA tensor the kernels do not cover (fp32, odd channel counts, tiny maps) raises
+with the bias epilogue); the encoder's stride-2 convolutions are the stride-1 kernel followed by a 2x sub-sampling; the
+softmax(QK^T)V core of the single 512-wide head of the mid-block attention is GEMM -> row softmax -> GEMM per image
+(``tld_vae_attention_core``).  There is NO silent fallback: a CUDA tensor the kernels do not cover (fp32, odd channel counts, tiny maps) raises
 ``TldError``; the plain ATen graph (what the CPU wiring tests and the fp32 oracle cross-check use) only runs when the module
 was built with ``allow_aten=True``.
 """
@@ -376,12 +376,21 @@ class AutoencoderKLDecoder(nn.Module):
         B, Cc, H, W = x.shape
         h = self._group_norm(x, name + ".group_norm", False)
         if self._on_kernels(x) and Cc % 32 == 0:
-            # projections on the tcgen05 GEMM; the softmax(QK^T)V core of this single Cc-wide head is the one library call
-            # of the decoder (module docstring)
+            # projections on the tcgen05 GEMM; the softmax(QK^T)V core of this single Cc-wide head: per image GEMM -> row
+            # softmax -> GEMM (tld_vae_attention_core)
+            from . import _lib
+
             t = self._rows(h)
-            q, k, v = (self._gemm_bias(t, f"{name}.{p}.weight", f"{name}.{p}.bias").view(B, 1, H * W, Cc) for p in ("to_q", "to_k", "to_v"))
-            o = F.scaled_dot_product_attention(q, k, v).reshape(B * H * W, Cc)
-            o = self._gemm_bias(o.contiguous(), name + ".to_out.0.weight", name + ".to_out.0.bias")
+            q, k, v = (self._gemm_bias(t, f"{name}.{p}.weight", f"{name}.{p}.bias") for p in ("to_q", "to_k", "to_v"))
+            if (H * W) % 64 == 0 and Cc % 64 == 0:
+                o = torch.empty_like(q)
+                _lib.check(_lib.load().tld_vae_attention_core(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, H * W, Cc,
+                                                              _lib.current_stream_ptr(x.device)), "tld_vae_attention_core")
+                self.own_launches += 3 * B
+            else:
+                self._aten(f"attention core {name}", x)
+                o = F.scaled_dot_product_attention(*(u.view(B, 1, H * W, Cc) for u in (q, k, v))).reshape(B * H * W, Cc).contiguous()
+            o = self._gemm_bias(o, name + ".to_out.0.weight", name + ".to_out.0.bias")
             return self._add_bias(x, self._from_rows(o, B, H, W))
         self._aten(f"attention {name}", x)
         t = h.permute(0, 2, 3, 1).reshape(B, H * W, Cc)
