@@ -371,3 +371,32 @@ def test_forward_with_fused_attention_kernels_on_and_off(img, D, L, B):
     for key, out in outs.items():
         assert rel_fro(out, ref) < TOL, f"{key}: rel_fro={rel_fro(out, ref):.3e}"
     assert rel_fro(outs[(1, 1)], outs[(0, 0)]) < TOL
+
+
+@pytest.mark.parametrize("img,D,L", [(32, 256, 2), (16, 128, 2), (64, 128, 1)])
+def test_sampler_shared_cfg_prefix_is_bit_identical(img, D, L):
+    """The CFG pair embeds the same x_t twice and only differs from the first cross-attention on: block 0's norm1 + self-attention
+    run once per pair and the rows are copied (option share_cfg_prefix).  Same bits as computing both halves."""
+    from transformer_latent_diffusion_b200 import _lib
+    from transformer_latent_diffusion_b200.diffusion import DiffusionGenerator
+
+    from oracle.ref_loader import IdentityVAE
+
+    cfg = O.OracleCfg(image_size=img, embed_dim=D, n_layers=L)
+    sd = O.synth_state_dict(cfg, 71)
+    m = _model(cfg, sd)
+    gen = DiffusionGenerator(m, IdentityVAE(), torch.device("cuda:0"), torch.float32)
+    g = torch.Generator().manual_seed(72)
+    seeds = torch.randn(3, 4, img, img, generator=g)
+    labels = torch.randn(3, 768, generator=g) * 2.0
+    outs = []
+    try:
+        for share in (1, 0, 1):
+            _lib.check(_lib.load().tld_set_option(b"share_cfg_prefix", share), "opt")
+            outs.append(gen.generate_latents(labels, n_iter=6, num_imgs=3, img_size=img, seeds=seeds, class_guidance=4.0).clone())
+    finally:
+        _lib.check(_lib.load().tld_set_option(b"share_cfg_prefix", 1), "opt")
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    with torch.no_grad():
+        ref = O.generate_latents(sd, cfg, labels, seeds, n_iter=6, class_guidance=4.0)
+    assert rel_fro(outs[0], ref) < 3 * TOL

@@ -1,6 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout -k 5 900 python -m pytest tests/test_vae.py tests/test_reference_suite_gpu.py -q --no-header -p no:cacheprovider -x 2>&1 | tail -8
-timeout -k 5 300 python tools/vae_profile.py > gpurun_out/vae_profile.txt 2>&1
-head -16 gpurun_out/vae_profile.txt | cut -c1-100,140-230 | grep -v "^-\|Warn\|_warn"
-tail -3 gpurun_out/vae_profile.txt
+timeout -k 5 600 python -m pytest tests/test_forward_gpu.py -q --no-header -p no:cacheprovider -x 2>&1 | tail -4
+for p in 1 0 1 0; do echo "share=$p"; timeout -k 5 300 python tools/time_forward.py --batch 64 --reps 3 --share-cfg $p | tail -2; done

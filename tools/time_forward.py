@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--fused-mlp", type=int, default=1)
     ap.add_argument("--fused-qkv", type=int, default=1)
     ap.add_argument("--qkv-emu", type=int, default=6)
+    ap.add_argument("--share-cfg", type=int, default=1)
     a = ap.parse_args()
     from transformer_latent_diffusion_b200 import _lib
     _lib.check(_lib.load().tld_set_option(b"gemm_ctas", a.gemm_ctas), "opt")
@@ -41,6 +42,7 @@ def main():
     _lib.check(_lib.load().tld_set_option(b"fused_mlp", a.fused_mlp), "opt")
     _lib.check(_lib.load().tld_set_option(b"fused_qkv", a.fused_qkv), "opt")
     _lib.check(_lib.load().tld_set_option(b"qkv_exp_emu", a.qkv_emu), "opt")
+    _lib.check(_lib.load().tld_set_option(b"share_cfg_prefix", a.share_cfg), "opt")
     torch.manual_seed(0)
     m = Denoiser(a.img, 256, 2, 768, 0, 12).cuda().eval()
     B2 = 2 * a.batch

@@ -296,6 +296,7 @@ static int ensure_fold(tld_denoiser* h, cudaStream_t st) {
 
 // the fused MLP front half needs one CTA-pair tile per sample (16x16 token grid) and whole 256-channel tiles
 static bool use_fused_mlp(const tld_denoiser* h) { return g_fused_mlp && h->G == 16 && h->H4 % 256 == 0; }
+static int g_share_cfg_prefix = 1;   // tld_set_option("share_cfg_prefix", ...): block 0's self-attention once per CFG pair (sampler)
 static int g_fused_xattn = 1;     // tld_set_option("fused_xattn", ...): norm2 + cross-attention + residual + norm3 in one row-wise kernel
 static bool use_fused_xattn(const tld_denoiser* h) {
   return g_fused_xattn && h->uk && ln_xattn_ln_supported(h->D, h->N) && !use_ln_fold(h);
@@ -314,10 +315,14 @@ static int g_fused_qkv = 1;       // tld_set_option("fused_qkv", ...): qkv proje
 static bool use_fused_qkv(const tld_denoiser* h) { return g_fused_qkv && h->N == 256 && !use_ln_fold(h); }
 
 // The L decoder blocks + output projection on the tokens already in h->x_res (transformer_blocks.py:135-139).
+// `distinct`: the residual rows of samples [distinct, batch) are copies of samples [0, distinct) on entry (the CFG pair embeds
+// the same x_t twice and differs only in the label token, i.e. from the first cross-attention on): block 0's norm1 +
+// self-attention then run on the distinct samples only and the result is copied.
 static int run_blocks(tld_denoiser* h, int batch, const float* kv0, long long kv0_stride, const float* kv1,
-                      long long kv1_stride, const int* step_ptr, float* out, cudaStream_t st) {
+                      long long kv1_stride, const int* step_ptr, float* out, cudaStream_t st, int distinct = 0) {
   const int D = h->D, H4 = h->H4, N = h->N;
   const int T = batch * N;
+  const bool share0 = g_share_cfg_prefix && distinct > 0 && distinct < batch && batch % distinct == 0 && !use_ln_fold(h);
   const bool fold = use_ln_fold(h);
   const int n_part = D / 32;
   int cur = 0;   // which xb / part buffer holds the current residual rows
@@ -329,13 +334,19 @@ static int run_blocks(tld_denoiser* h, int batch, const float* kv0, long long kv
     if (fold) {   // norm1 folded: A = bf16(x), W = gamma (.) Wqkv, mean / rstd applied on the accumulator
       LnFoldArgs ln{fl.s_qkv, h->part[cur], n_part, 1e-5f, nullptr, 0, nullptr};
       if (launch_gemm(EPI_LNFOLD_BF16, h->xb[cur], D, fl.wqkv_f, D, T, 3 * D, D, h->qkv, 3 * D, fl.c_qkv, nullptr, st, &ln)) return 1;
-    } else {
-      if (launch_layernorm_bf16(h->x_res, ly.ln1w, ly.ln1b, h->xn, T, D, st)) return 1;
-      if (!use_fused_qkv(h) && launch_gemm(EPI_BF16, h->xn, D, ly.wqkv, D, T, 3 * D, D, h->qkv, 3 * D, nullptr, nullptr, st)) return 1;
+    }
+    const int ab = (l == 0 && share0) ? distinct : batch;   // samples the self-attention of this block runs on
+    const int Ta = ab * N;
+    if (!fold) {
+      if (launch_layernorm_bf16(h->x_res, ly.ln1w, ly.ln1b, h->xn, Ta, D, st)) return 1;
+      if (!use_fused_qkv(h) && launch_gemm(EPI_BF16, h->xn, D, ly.wqkv, D, Ta, 3 * D, D, h->qkv, 3 * D, nullptr, nullptr, st)) return 1;
     }
     if (use_fused_qkv(h)) {   // the CTA pair that owns a (sample, head) projects q, k, v itself: qkv never touches HBM
-      if (launch_qkv_attention(h->xn, ly.wqkv, h->x_res, batch, N, D, st)) return 1;
-    } else if (launch_self_attention(h->qkv, h->x_res, batch, N, D, st, g_attention_impl)) return 1;
+      if (launch_qkv_attention(h->xn, ly.wqkv, h->x_res, ab, N, D, st)) return 1;
+    } else if (launch_self_attention(h->qkv, h->x_res, ab, N, D, st, g_attention_impl)) return 1;
+    if (ab != batch)
+      for (int c = 1; c < batch / distinct; ++c)
+        TLD_CUDA_OK(cudaMemcpyAsync(h->x_res + (size_t)c * Ta * D, h->x_res, sizeof(float) * (size_t)Ta * D, cudaMemcpyDeviceToDevice, st));
     // x = CrossAttention(LN2(x), y) + x
     if (use_fused_xattn(h)) {   // norm2, the (folded) q projection, the 2-key softmax, the residual and norm3 in one row-wise pass
       const long long kvs_all = (long long)h->L * 2 * D, uks = (long long)h->L * (D / 64) * D;
@@ -431,6 +442,10 @@ int tld_set_option(const char* key, int value) {
   if (k == "qkv_exp_emu") {
     TLD_CHECK(value == 0 || value == 4 || value == 6 || value == 8, "qkv_exp_emu (exp2 pairs per 16 on the FMA pipe, fused qkv + attention kernel) must be 0, 4, 6 or 8");
     set_qkv_attention_exp_emu(value);
+    return 0;
+  }
+  if (k == "share_cfg_prefix") {
+    g_share_cfg_prefix = value != 0;
     return 0;
   }
   if (k == "fused_xattn") {
@@ -749,7 +764,7 @@ int tld_sampler_generate(tld_denoiser* h, const float* labels, const float* seed
     cudaGraph_t graph = nullptr;
     TLD_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     int rc = launch_embed(h->x_t, num_imgs, Beff, h->C, h->img, h->patch, h->D, h->emb, h->x_res, st);
-    if (!rc) rc = run_blocks(h, Beff, kv0, kvs /*row = *step_ptr*/, kv1, kvs, h->step_ptr, h->model_out, st);
+    if (!rc) rc = run_blocks(h, Beff, kv0, kvs /*row = *step_ptr*/, kv1, kvs, h->step_ptr, h->model_out, st, num_imgs);
     if (!rc)
       rc = launch_cfg_update(h->model_out, h->x_t, h->x0_prev, h->x0_out, h->step_table, h->step_ptr, num_imgs, h->C,
                              h->img * h->img, st);
