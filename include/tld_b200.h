@@ -55,7 +55,11 @@ TLD_API int tld_version(void);
  * "fused_mlp" = 1 (default) up-projection + depthwise conv + GELU as one
  * kernel for 16x16 token grids | 0 three separate kernels;  "ln_fold" = 1 norm1 / norm3 folded into the neighbouring GEMMs (their
  * statistics ride on the residual epilogues; measured slower on B200, see csrc/api.cu) | 0 (default) separate LayerNorm kernels;  "pdl" = 1 launch
- * the step kernels with programmatic dependent launch (prologues overlap the previous kernel's tail) | 0 plain launches (default: measured no gain). */
+ * the step kernels with programmatic dependent launch (prologues overlap the previous kernel's tail) | 0 plain launches (default: measured no gain);
+ * "fused_qkv" = 1 (default) qkv projection + self-attention + residual as one CTA-pair kernel at 256 tokens per sample | 0 GEMM + attention kernel;
+ * "qkv_exp_emu" = 0|4|6|8 the same exp2 split for that kernel;  "fused_xattn" = 1 (default) norm2 + 2-token cross-attention (q folded into the keys)
+ * + residual + norm3 as one row-wise kernel (embed_dim % 128 == 0) | 0 LayerNorm, q GEMM with the 2-key epilogue, LayerNorm;
+ * "share_cfg_prefix" = 1 (default) the sampler runs block 0's norm1 + self-attention once per CFG pair and copies the rows (bit-identical) | 0. */
 TLD_API int tld_set_option(const char* key, int value);
 
 /* ---- lifetime --------------------------------------------------------------------------------
