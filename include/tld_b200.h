@@ -59,6 +59,9 @@ TLD_API int tld_version(void);
  * "fused_qkv" = 1 (default) qkv projection + self-attention + residual as one CTA-pair kernel at 256 tokens per sample | 0 GEMM + attention kernel;
  * "qkv_exp_emu" = 0|4|6|8 the same exp2 split for that kernel;  "fused_xattn" = 1 (default) norm2 + 2-token cross-attention (q folded into the keys)
  * + residual + norm3 as one row-wise kernel (embed_dim % 128 == 0) | 0 LayerNorm, q GEMM with the 2-key epilogue, LayerNorm;
+ * variants of that row kernel, all measured within 10 % of each other: "xattn_rows" = 4 (default) | 2 rows per warp
+ * (8 | 16 warps), "xattn_ctas" = 1 (default) | 2 CTAs per SM, "xattn_mma" = 0 (default) FFMA dot products | 1 | 2 | 3 the dots as
+ * tf32 mma.sync with x truncated | x split hi + lo | x and the folded keys split (embed_dim <= 768, tokens % 8 == 0);
  * "share_cfg_prefix" = 1 (default) the sampler runs block 0's norm1 + self-attention once per CFG pair and copies the rows (bit-identical) | 0. */
 TLD_API int tld_set_option(const char* key, int value);
 

@@ -32,6 +32,9 @@ def main():
     ap.add_argument("--fused-qkv", type=int, default=1)
     ap.add_argument("--qkv-emu", type=int, default=6)
     ap.add_argument("--share-cfg", type=int, default=1)
+    ap.add_argument("--xattn-mma", type=int, default=0)
+    ap.add_argument("--xattn-rows", type=int, default=4)
+    ap.add_argument("--xattn-ctas", type=int, default=1)
     a = ap.parse_args()
     from transformer_latent_diffusion_b200 import _lib
     _lib.check(_lib.load().tld_set_option(b"gemm_ctas", a.gemm_ctas), "opt")
@@ -43,6 +46,9 @@ def main():
     _lib.check(_lib.load().tld_set_option(b"fused_qkv", a.fused_qkv), "opt")
     _lib.check(_lib.load().tld_set_option(b"qkv_exp_emu", a.qkv_emu), "opt")
     _lib.check(_lib.load().tld_set_option(b"share_cfg_prefix", a.share_cfg), "opt")
+    _lib.check(_lib.load().tld_set_option(b"xattn_mma", a.xattn_mma), "opt")
+    _lib.check(_lib.load().tld_set_option(b"xattn_rows", a.xattn_rows), "opt")
+    _lib.check(_lib.load().tld_set_option(b"xattn_ctas", a.xattn_ctas), "opt")
     torch.manual_seed(0)
     m = Denoiser(a.img, 256, 2, 768, 0, 12).cuda().eval()
     B2 = 2 * a.batch

@@ -56,6 +56,15 @@ def timeit(fn, name):
 
 
 if a.mode in ("all", "fused"):
-    timeit(fused, "fold keys (2 launches) + fused norm2/xattn/norm3")
+    for rows, ctas in ((4, 1), (4, 2), (2, 1), (2, 2), (4, 1), (4, 2)):   # FFMA row kernel: rows per warp, CTAs per SM
+        _lib.check(L.tld_set_option(b"xattn_rows", rows), "opt")
+        _lib.check(L.tld_set_option(b"xattn_ctas", ctas), "opt")
+        timeit(fused, f"fold keys (2 launches) + fused norm2/xattn/norm3, xattn_rows={rows} xattn_ctas={ctas}")
+    for mma in (1, 2, 3):   # tf32 mma.sync dots (x truncated / x split / x and keys split)
+        _lib.check(L.tld_set_option(b"xattn_mma", mma), "opt")
+        timeit(fused, f"fold keys (2 launches) + fused norm2/xattn/norm3, xattn_mma={mma}")
+    _lib.check(L.tld_set_option(b"xattn_mma", 0), "opt")
+    _lib.check(L.tld_set_option(b"xattn_rows", 4), "opt")
+    _lib.check(L.tld_set_option(b"xattn_ctas", 1), "opt")
 if a.mode in ("all", "split"):
     timeit(split, "layernorm + q GEMM with 2-key epilogue + layernorm")

@@ -452,6 +452,21 @@ int tld_set_option(const char* key, int value) {
     g_fused_xattn = value != 0;
     return 0;
   }
+  if (k == "xattn_rows") {
+    TLD_CHECK(value == 2 || value == 4, "xattn_rows (rows per warp of the norm2 + cross-attention + norm3 row kernel) must be 2 or 4");
+    set_xattn_rows(value);
+    return 0;
+  }
+  if (k == "xattn_ctas") {
+    TLD_CHECK(value == 1 || value == 2, "xattn_ctas (CTAs per SM of the norm2 + cross-attention + norm3 row kernel) must be 1 or 2");
+    set_xattn_ctas(value);
+    return 0;
+  }
+  if (k == "xattn_mma") {
+    TLD_CHECK(value >= 0 && value <= 3, "xattn_mma must be 0 (FFMA row kernel, default), 1 (tf32 mma.sync dots, x rounded), 2 (x split) or 3 (x and folded keys split)");
+    set_xattn_mma(value);
+    return 0;
+  }
   if (k == "fused_qkv") {
     g_fused_qkv = value != 0;
     return 0;

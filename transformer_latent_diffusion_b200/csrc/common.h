@@ -163,6 +163,9 @@ int launch_self_attention_tc2(const bf16* qkv, float* x, int B, int n_tok, int D
 int launch_xattn_fold_keys(const float* kv, long long kv_stride, int R, const bf16* wq, float* uk, long long uk_stride, int D,
                            cudaStream_t st);
 bool ln_xattn_ln_supported(int D, int n_tok);
+void set_xattn_rows(int v);  // rows per warp of the FFMA row kernel: 4 (8 warps x 255 registers) or 2 (16 warps x 128)
+void set_xattn_ctas(int v);  // CTAs per SM of the FFMA row kernel: 1 (32 / rows warps) or 2 (half the warps each)
+void set_xattn_mma(int v);   // 0 = FFMA row kernel, 1 / 2 / 3 = tensor-pipe dot products (tf32 mma.sync), x rounded / x split / x and keys split
 int launch_ln_xattn_ln(float* x, const float* g2, const float* b2, const float* g3, const float* b3, const float* uk0,
                        long long uk0_stride, const float* uk1, long long uk1_stride, const float* kv0, long long kv0_stride,
                        const float* kv1, long long kv1_stride, const int* step_ptr, bf16* y, int rows, int n_tok, int D,
