@@ -336,27 +336,42 @@ __global__ void __launch_bounds__(xl_warps(R, CT) * 32, CT) ln_xattn_ln_kernel(X
       acc[r] = q;
     }
     const float rstd_mine = rsqrtf(reduce_rows<R>(acc, lane) * (1.f / D) + LN_EPS);
-    // ---- per head: dlt = LN2(x) . (u0 - u1), p0 = sigmoid(dlt / 8); the lane keeps p0 of the heads its columns belong to
+    // ---- per head: dlt = LN2(x) . (u0 - u1), p0 = sigmoid(dlt / 8); the lane keeps p0 of the heads its columns belong to.
+    // Heads go in batches of HB: first the dots of the batch, then its HB transpose-reductions side by side (independent
+    // shuffle chains: one round trip of latency per stage for the whole batch), then the sigmoids with an approximate
+    // reciprocal.  Head by head, every head ended in six dependent shuffle round trips and an IEEE division whose slow-path
+    // branch (BSSY / BSYNC) kept ptxas from overlapping anything with the next head: ~250 exposed cycles per head.
+    constexpr int HB = H % 6 == 0 ? 6 : (H % 4 == 0 ? 4 : 2);
     float p0h[H];   // p0 of the row this lane owns after reduce_rows, for every head; broadcast when the columns are updated
 #pragma unroll
-    for (int h = 0; h < H; ++h) {
-      float2 a2[R];   // packed fp32 FMA (FFMA2): half the issue slots of the dot products
+    for (int h0 = 0; h0 < H; h0 += HB) {
+      float part[HB][R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) a2[r] = make_float2(0.f, 0.f);
+      for (int hh = 0; hh < HB; ++hh) {
+        const int h = h0 + hh;
+        float2 a2[R];   // packed fp32 FMA (FFMA2): half the issue slots of the dot products
 #pragma unroll
-      for (int j = 0; j < V; ++j) {
-        const float4 d = dl[h * D4 + lane + 32 * j];
+        for (int r = 0; r < R; ++r) a2[r] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          a2[r] = ffma2(make_float2(xv[r][j].x, xv[r][j].y), make_float2(d.x, d.y), a2[r]);
-          a2[r] = ffma2(make_float2(xv[r][j].z, xv[r][j].w), make_float2(d.z, d.w), a2[r]);
+        for (int j = 0; j < V; ++j) {
+          const float4 d = dl[h * D4 + lane + 32 * j];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            a2[r] = ffma2(make_float2(xv[r][j].x, xv[r][j].y), make_float2(d.x, d.y), a2[r]);
+            a2[r] = ffma2(make_float2(xv[r][j].z, xv[r][j].w), make_float2(d.z, d.w), a2[r]);
+          }
         }
-      }
 #pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = a2[r].x + a2[r].y;
-      const float tot = reduce_rows<R>(acc, lane);
-      const float dlt = rstd_mine * (tot - mean_mine * hs[h]) + hc[h];
-      p0h[h] = 1.f / (1.f + __expf(-dlt * scale));
+        for (int r = 0; r < R; ++r) part[hh][r] = a2[r].x + a2[r].y;
+      }
+      float tot[HB];
+#pragma unroll
+      for (int hh = 0; hh < HB; ++hh) tot[hh] = reduce_rows<R>(part[hh], lane);
+#pragma unroll
+      for (int hh = 0; hh < HB; ++hh) {
+        const float dlt = rstd_mine * (tot[hh] - mean_mine * hs[h0 + hh]) + hc[h0 + hh];
+        p0h[h0 + hh] = __fdividef(1.f, 1.f + __expf(-dlt * scale));
+      }
     }
     // ---- x_new = x + v1 + p0 (v0 - v1); norm3 statistics
 #pragma unroll
@@ -622,13 +637,13 @@ __global__ void __launch_bounds__(XM_WARPS * 32, 1) ln_xattn_ln_mma_kernel(XlArg
         __syncwarp();   // the previous group's readers of the scratch are done
         if (g < H) {
           const float hsv = hs[g], hcv = hc[g];
-          pww[(2 * t) * XM_PSTRIDE + g] = 1.f / (1.f + __expf(-(rstd_a * (tot[0] - mean_a * hsv) + hcv) * scale));
-          pww[(2 * t + 1) * XM_PSTRIDE + g] = 1.f / (1.f + __expf(-(rstd_b * (tot[1] - mean_b * hsv) + hcv) * scale));
+          pww[(2 * t) * XM_PSTRIDE + g] = __fdividef(1.f, 1.f + __expf(-(rstd_a * (tot[0] - mean_a * hsv) + hcv) * scale));
+          pww[(2 * t + 1) * XM_PSTRIDE + g] = __fdividef(1.f, 1.f + __expf(-(rstd_b * (tot[1] - mean_b * hsv) + hcv) * scale));
         }
         if (g + 8 < H) {
           const float hsv = hs[g + 8], hcv = hc[g + 8];
-          pww[(2 * t) * XM_PSTRIDE + g + 8] = 1.f / (1.f + __expf(-(rstd_a * (tot[2] - mean_a * hsv) + hcv) * scale));
-          pww[(2 * t + 1) * XM_PSTRIDE + g + 8] = 1.f / (1.f + __expf(-(rstd_b * (tot[3] - mean_b * hsv) + hcv) * scale));
+          pww[(2 * t) * XM_PSTRIDE + g + 8] = __fdividef(1.f, 1.f + __expf(-(rstd_a * (tot[2] - mean_a * hsv) + hcv) * scale));
+          pww[(2 * t + 1) * XM_PSTRIDE + g + 8] = __fdividef(1.f, 1.f + __expf(-(rstd_b * (tot[3] - mean_b * hsv) + hcv) * scale));
         }
         __syncwarp();
       }
