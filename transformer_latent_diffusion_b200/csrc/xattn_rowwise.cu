@@ -228,6 +228,15 @@ __device__ __forceinline__ void bcast_rows(float mine, int lane, float (&out)[R]
   for (int r = 0; r < R; ++r)
     out[r] = __shfl_sync(0xffffffffu, mine, R == 4 ? (r >> 1) * 16 + (r & 1) * 8 + (lane & 7) : r * 16 + (lane & 15));
 }
+// Two values per owner group in ONE shuffle: the owner lanes with bit 2 clear offer `lo`, those with bit 2 set offer `hi`;
+// lanes 0..15 fetch row r's `lo`, lanes 16..31 its `hi` (every lane of an owner group holds both).
+template <int R>
+__device__ __forceinline__ void bcast_rows_split(float lo, float hi, int lane, float (&out)[R]) {
+  const float mine = (lane & 4) ? hi : lo;
+  const int sub = ((lane >> 4) & 1) * 4 + (lane & 3);
+#pragma unroll
+  for (int r = 0; r < R; ++r) out[r] = __shfl_sync(0xffffffffu, mine, R == 4 ? (r >> 1) * 16 + (r & 1) * 8 + sub : r * 16 + sub);
+}
 
 // R rows per warp, 32 / R warps.  R = 4: 8 warps x 255 registers, every dl element read from shared memory feeds 4 rows.
 // (12 warps x 4 rows at 168 registers spilled 250 B at D = 768 and measured slower: 75.5 against 68.6 us.)
@@ -271,6 +280,7 @@ __global__ void __launch_bounds__(xl_warps(R, CT) * 32, CT) ln_xattn_ln_kernel(X
   fence_mbar_init();
   __syncthreads();
   pdl_wait();
+  const long long step_row = a.step_ptr ? (long long)(*a.step_ptr) : 0;   // one dependent load per kernel, not per table build
   float4* my_buf = rowbuf + warp * R * D4;
   auto seg_end_of = [&](int g) { const int e = (g / gps + 1) * gps; return e < G1 ? e : G1; };
   auto first_from = [&](int s) {   // first group >= segment start s that belongs to this warp, or -1
@@ -297,7 +307,7 @@ __global__ void __launch_bounds__(xl_warps(R, CT) * 32, CT) ln_xattn_ln_kernel(X
     const int b = seg / gps;
     {   // the sample's tables
       __syncthreads();  // every warp is done with the previous sample's tables
-      const long long r0 = a.step_ptr ? (long long)(*a.step_ptr) : (long long)b;
+      const long long r0 = a.step_ptr ? step_row : (long long)b;
       xl_build_tables<V, NT, 0>(a, r0, b, g2s, b2s, reinterpret_cast<float*>(dl), nullptr, v1, dv, hs, hc, part);
     }
     // ---- this warp's groups of the segment
@@ -380,12 +390,11 @@ __global__ void __launch_bounds__(xl_warps(R, CT) * 32, CT) ln_xattn_ln_kernel(X
     for (int j = 0; j < V; ++j) {
       const float4 q = v1[lane + 32 * j], d = dv[lane + 32 * j];
       // columns 128 j + 4 lane .. lie in head 2 j + (lane >= 16): fetch that head's p0 of every row from the lanes that own the row
-      float pa[R], pb[R];
-      bcast_rows<R>(p0h[2 * j], lane, pa);
-      bcast_rows<R>(p0h[2 * j + 1], lane, pb);
+      float pab[R];   // lanes 0..15: p0 of head 2 j, lanes 16..31: of head 2 j + 1, for every row (one shuffle per row)
+      bcast_rows_split<R>(p0h[2 * j], p0h[2 * j + 1], lane, pab);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const float pr = (lane & 16) ? pb[r] : pa[r];
+        const float pr = pab[r];
         xv[r][j].x += fmaf(pr, d.x, q.x);
         xv[r][j].y += fmaf(pr, d.y, q.y);
         xv[r][j].z += fmaf(pr, d.z, q.z);
