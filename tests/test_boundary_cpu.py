@@ -47,6 +47,28 @@ def test_no_cuda_means_loud_failure(built_lib):
     assert b"no CUDA device" in lib.tld_last_error()
 
 
+def test_set_option_validates_keys_and_values(built_lib):
+    """tld_set_option is host-only: every documented key is accepted with its documented values, anything else is an error
+    with a message (no silent no-op).  Values are restored to the defaults the header documents."""
+    from transformer_latent_diffusion_b200 import _lib
+
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "tld_b200.h")).read()
+    good = {b"gemm_ctas": (0, 1, 2, 0), b"attention_impl": (1, 3, 0), b"attention_bwd_impl": (2, 1, 0), b"fused_mlp": (0, 1),
+            b"fused_qkv": (0, 1), b"fused_xattn": (0, 1), b"share_cfg_prefix": (0, 1), b"ln_fold": (1, 0), b"pdl": (1, 0),
+            b"qkv_exp_emu": (0, 4, 8, 6), b"xattn_rows": (2, 4), b"xattn_ctas": (2, 1), b"xattn_mma": (1, 2, 3, 0)}
+    for key, values in good.items():
+        assert key.decode() in header, f"option {key!r} is not documented in include/tld_b200.h"
+        for v in values:
+            assert lib.tld_set_option(key, v) == 0, (key, v, lib.tld_last_error())
+    bad = [(b"xattn_rows", 3), (b"xattn_ctas", 0), (b"xattn_mma", 4), (b"gemm_ctas", 3), (b"attention_impl", 2), (b"qkv_exp_emu", 5),
+           (b"no_such_option", 1)]
+    for key, v in bad:
+        assert lib.tld_set_option(key, v) != 0, (key, v)
+        assert lib.tld_last_error()
+    assert lib.tld_set_option(None, 0) != 0
+
+
 def test_denoiser_signature_and_state_dict():
     from transformer_latent_diffusion_b200.configs import DenoiserConfig
     from transformer_latent_diffusion_b200.denoiser import Denoiser

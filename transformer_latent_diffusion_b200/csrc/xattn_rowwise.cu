@@ -79,6 +79,12 @@ struct XlArgs {
   int rows, n_tok;
 };
 
+__device__ __forceinline__ uint32_t tf32_rna(float f) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(f));
+  return u;
+}
+
 // Per-sample tables of both row kernels -> shared memory: dl_h = gamma2 (u0 - u1)_h per head, the per-head constants
 // hs = sum_c dl_h[c] and hc = sum_c beta2[c] (u0 - u1)_h[c], v1 and v0 - v1.  Every thread issues ALL its global loads first
 // (one memory latency per build; the per-head loop of the first version paid three in a row and idled half the warps on its
@@ -131,9 +137,7 @@ __device__ __forceinline__ void xl_build_tables(const XlArgs& a, long long r0, i
           hi[e] = o[e];
           lo[e] = 0.f;
         } else if (MODE == 1) {
-          uint32_t u;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(o[e]));
-          hi[e] = __uint_as_float(u);
+          hi[e] = __uint_as_float(tf32_rna(o[e]));
           lo[e] = 0.f;
         } else {
           hi[e] = __uint_as_float(__float_as_uint(o[e]) & HI_MASK);
@@ -462,11 +466,6 @@ __global__ void __launch_bounds__(xl_warps(R, CT) * 32, CT) ln_xattn_ln_kernel(X
 // (twice the L1 wavefronts of the row-per-warp layout) and exposes the row loads (24 % of the samples in long_scoreboard,
 // 22 % in the store phase).  Loading the next group chunk by chunk behind the stores of the current one made it worse
 // (82 us).  Kept as an option (xattn_mma = 1 / 2 / 3), off by default.
-__device__ __forceinline__ uint32_t tf32_rna(float f) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(f));
-  return u;
-}
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                                 uint32_t b1) {
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
