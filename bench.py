@@ -409,7 +409,7 @@ def run_b200(args) -> None:
                                "attention, norm2 + folded 2-token cross-attention + norm3, fused up-projection + depthwise conv + "
                                "GELU, down-projection + residual)",
                    "vae_decode": "libtld_b200 tcgen05 implicit-GEMM conv3x3 + fused GroupNorm/SiLU/upsample kernels (bf16); parity "
-                                 "UNPINNED (third-party diffusers absent: checked against oracle/vae_oracle.py only)"},
+                                 "UNPINNED to diffusers (third-party, absent): checked against oracle/vae_oracle.py, which is cross-checked against torchtitan's LDM AutoEncoder (same architecture) on random weights"},
         "denoiser_step_ms": loop_ms / N_ITER, "denoiser_only_images_per_s_per_gpu": B / (loop_ms * 1e-3),
         "denoiser_step_frac_of_sustained_bf16_peak": step_flops / (loop_ms / N_ITER * 1e-3) / 1e12 / sustained,
         "flops_accounting": "SURVEY.md 8d model FLOPs of the reference's formulation (24 n d^2 + ... per block); the folded "

@@ -1,12 +1,16 @@
 """fp32 CPU restatement of the SDXL AutoencoderKL *decoder* (third-party: `diffusers`, unpinned in the
 reference's pyproject.toml:26; weights `madebyollin/sdxl-vae-fp16-fix`, tld/configs.py:42).  TEST INFRA ONLY.
 
-PARITY UNPINNED: neither `diffusers` nor the weights exist in this environment, and the reference's tests that
-touch the VAE assert no values.  This file restates the published decoder algorithm
+PARITY NOT PINNED TO DIFFUSERS: neither `diffusers` nor the weights exist in this environment, and the reference's tests
+that touch the VAE assert no values.  This file restates the published decoder algorithm
 (GroupNorm(32, eps 1e-6) -> SiLU -> conv3x3 ResNet blocks, one single-head attention in the mid block,
 nearest-2x upsampling + conv3x3, final GroupNorm/SiLU/conv) directly from tensors in a diffusers-keyed
 state_dict, written independently of transformer_latent_diffusion_b200/vae.py (no nn.Module, explicit
 GroupNorm/softmax) so the two can be compared on random weights.  Call sites: tld/diffusion.py:91.
+CROSS-CHECKED against an independent third-party implementation of the same network that IS in the image: torchtitan's
+FLUX `AutoEncoder` (the CompVis / LDM autoencoder diffusers' AutoencoderKL ports), encoder and decoder, random weights
+renamed with diffusers' published LDM key map, fp32, 1e-5 (tests/test_vae_oracle_crosscheck.py).  That verifies the
+architecture restatement, not diffusers' code or the sdxl-vae-fp16-fix weights.
 """
 from __future__ import annotations
 
@@ -74,7 +78,7 @@ def decode(sd, z, n_up_blocks=4, layers_per_block=2):
 
 # ---------------------------------------------------------------------------------------------------------------
 # Encoder half (call sites tld/data.py:35-41,168).  Same status as the decoder: third-party
-# diffusers code, PARITY UNPINNED; restated from the published AutoencoderKL encoder (conv_in 3->128, four down blocks of
+# diffusers code, not pinned to diffusers (cross-checked against the LDM AutoEncoder, see the header); restated from the published AutoencoderKL encoder (conv_in 3->128, four down blocks of
 # two ResNets with an asymmetric-pad stride-2 conv between them, mid block with one single-head attention,
 # GroupNorm/SiLU/conv_out to 2*latent channels, 1x1 quant_conv, diagonal Gaussian with logvar clamped to [-30, 20]).
 # ---------------------------------------------------------------------------------------------------------------
